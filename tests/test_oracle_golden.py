@@ -1,0 +1,88 @@
+"""CPU: the oracle (numpy restatement + ATen port) against fixtures recorded from the real reference."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+from oracle import aten_port, blob_oracle
+
+CASES = G.cases()
+IDS = [c["name"] for c in CASES]
+
+
+def _tol(case, key, want):
+    f64 = want.dtype == np.float64 and not case["name"].endswith("_f32")
+    if key == "feature_img_moments":
+        return (1e-9, 0) if f64 else (2e-5, 0)
+    if f64:
+        return 1e-9, 1e-13
+    # fp32: closed-form inverse vs the reference's pivoted LU differ on near-zero tails;
+    # scores live in [0,1] so 1e-5 scale-relative == abs 1e-5; thin blobs are "numerics only" (6.7e-6 seen)
+    return 1e-5, 1e-5
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_numpy_oracle_matches_reference(case):
+    for key, got, want in G.run_case(case, blob_oracle):
+        rtol, atol = _tol(case, key, want)
+        if "feature" in key or key == "ret" and case["func"] != "splat_features":
+            atol = max(atol, atol * float(np.abs(want).max()))
+        assert got.dtype == want.dtype or key == "feature_img_moments", (key, got.dtype, want.dtype)
+        G.check_close(got, want, rtol, atol, f"{case['name']}:{key}")
+
+
+class _Port:
+    splat_features = staticmethod(aten_port.render)
+    splat_features_from_scores = staticmethod(aten_port.feature_splat)
+    pyramid_resize = staticmethod(aten_port.halve_pyramid)
+
+
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_aten_port_matches_reference(case):
+    """Same ATen kernels as the reference -> equal up to CPU-ISA dispatch differences."""
+    torch.set_num_threads(1)
+    for key, got, want in G.run_case(case, _Port, wrap=torch.from_numpy, to_np=lambda t: t.detach().numpy()):
+        f64 = want.dtype == np.float64 and not case["name"].endswith("_f32")
+        if key == "feature_img_moments":      # recorded with torch's fp32 reductions
+            G.check_close(got, want, 1e-9 if f64 else 2e-5, 0, f"{case['name']}:{key}")
+            continue
+        G.check_close(got, want, 1e-12 if f64 else 2e-6, 1e-15 if f64 else 1e-7, f"{case['name']}:{key}")
+
+
+def test_forty_demo_ellipses_fp64():
+    """All 40 state.json ellipses through the script recipe (blobctrl_inference.py:71-117)."""
+    want = G.arrays()["ellipses/fg64"]
+    ell = G.ellipses()
+    assert len(ell) == 40 and want.shape == (40, 64, 64)
+    for i, e in enumerate(ell):
+        blob = blob_oracle.blob_from_ellipse(e["ellipse"], 512, 512)
+        d = blob_oracle.splat_features(**blob, score_size=(64, 64), return_d_score=True)
+        assert d.shape == (1, 2, 64, 64) and d.dtype == np.float64
+        G.check_close(d[0, 1], want[i], 1e-9, 1e-13, f"{e['demo']}[{e['idx']}] fg")
+        G.check_close(d[0, 0], 1 - want[i], 1e-9, 1e-13, f"{e['demo']}[{e['idx']}] bg")
+    # the two degenerate (1e-5, 1e-5) ellipses: exactly one pixel = 1.0 (SURVEY probe B7)
+    for i, e in enumerate(ell):
+        if e["ellipse"][1] == [1e-05, 1e-05]:
+            assert (want[i] == 1.0).sum() == 1 and (want[i] > 0).sum() == 1
+
+
+def test_invariants():
+    syn = blob_oracle.synthetic_blobs(2, 16, seed=7)
+    raw = blob_oracle.raw_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], 32, 32, np.float64)
+    s, d = blob_oracle.composite(raw)
+    assert np.allclose(d.sum(-1), 1.0, atol=1e-12)                      # partition of unity
+    gone = syn["sizes"] < 0.5
+    assert np.all(raw[:, :, :, :][..., gone[0]][0] == np.float64(np.float32(1e-6)))
+    one = blob_oracle.synthetic_blobs(1, 1, seed=8); one["sizes"][:] = 1
+    d1 = blob_oracle.render_scores(one["xs"], one["ys"], one["covs"], one["sizes"], 16, 16)
+    assert np.array_equal(d1[:, 0], 1 - d1[:, 1])                       # M=1: bg = 1 - fg
+
+
+def test_tuple_size_requires_single_blob():
+    syn = blob_oracle.synthetic_blobs(2, 3, seed=9)
+    with pytest.raises(RuntimeError):
+        blob_oracle.splat_features(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], score_size=(8, 8),
+                                   return_d_score=True)
+    t = {k: torch.from_numpy(v) for k, v in syn.items()}
+    with pytest.raises(RuntimeError):
+        aten_port.render(t["xs"], t["ys"], t["covs"], t["sizes"], score_size=(8, 8), return_d_score=True)
