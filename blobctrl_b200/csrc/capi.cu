@@ -1,0 +1,159 @@
+// extern "C" surface of libblobsplat.so — argument validation, device guard, dispatch.
+// Declarations and the reference interfaces each entry replaces: include/blobsplat.h.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace blobsplat {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return BLOBSPLAT_E_CUDA;
+}
+
+// kernels' host-side dispatchers (scores.cu, resize.cu, feature_splat.cu, render_tc.cu)
+int scores_dispatch(const void*, const void*, const void*, const float*, int, int, int, int, int, int, void*, int,
+                    void*, int, int, cudaStream_t);
+int composite_dispatch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int resize_dispatch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int pyramid_dispatch(const void*, void* const*, int, int, int, int, cudaStream_t);
+int feature_splat_fma_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int,
+                               int, cudaStream_t);
+int render_tc_dispatch(const float*, const float*, const float*, const float*, const void*, int, int, int, int, int,
+                       int, void*, void*, int, cudaStream_t);
+int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why);
+void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
+
+constexpr int kMaxBlobs = 1 << 20;
+
+static bool valid_dtype(int dt) { return dt >= BLOBSPLAT_F32 && dt <= BLOBSPLAT_F16; }
+
+}  // namespace blobsplat
+
+using namespace blobsplat;
+
+extern "C" {
+
+int blobsplat_abi_version(void) { return BLOBSPLAT_ABI_VERSION; }
+
+int blobsplat_get_caps(blobsplat_caps* out) {
+  BS_CHECK_ARG(out != nullptr, "caps pointer is NULL");
+  out->abi_version = BLOBSPLAT_ABI_VERSION;
+  out->sm_arch = 100;
+  out->max_blobs = kMaxBlobs;
+  render_tc_limits(&out->tensor_max_k, &out->tensor_c_multiple, &out->tensor_max_c);
+  return BLOBSPLAT_OK;
+}
+
+int blobsplat_last_error(char* buf, size_t cap) {
+  const size_t len = strlen(g_err);
+  if (buf && cap) {
+    const size_t n = len < cap - 1 ? len : cap - 1;
+    memcpy(buf, g_err, n);
+    buf[n] = 0;
+  }
+  return (int)len;
+}
+
+int blobsplat_scores(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype, int N,
+                     int M, int H, int W, int select, void* composed, int composed_dtype, void* raw, int raw_dtype,
+                     int composite_mode, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1, "bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+  BS_CHECK_ARG(M <= kMaxBlobs, "M=%d exceeds max_blobs=%d", M, kMaxBlobs);
+  BS_CHECK_ARG((long long)H * W < (1ll << 31), "H*W must fit in int32");
+  BS_CHECK_ARG(N <= 65535, "N=%d exceeds the grid limit 65535; split the batch", N);
+  BS_CHECK_ARG(select >= BLOBSPLAT_SELECT_ALL && select <= BLOBSPLAT_SELECT_BG, "bad select %d", select);
+  BS_CHECK_ARG(composite_mode >= BLOBSPLAT_COMPOSITE_AUTO && composite_mode <= BLOBSPLAT_COMPOSITE_WARP_SCAN,
+               "bad composite_mode %d", composite_mode);
+  BS_CHECK_ARG(composed || raw, "both outputs are NULL");
+  BS_CHECK_ARG(!composed || valid_dtype(composed_dtype), "bad composed dtype %d", composed_dtype);
+  BS_CHECK_ARG(!raw || valid_dtype(raw_dtype), "bad raw dtype %d", raw_dtype);
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return scores_dispatch(xs, ys, covs, sizes, param_dtype, N, M, H, W, select, composed, composed_dtype, raw,
+                         raw_dtype, composite_mode, (cudaStream_t)stream);
+}
+
+int blobsplat_composite(const void* scores_in, void* composed, int N, int K, int H, int W, int dtype, int device,
+                        void* stream) {
+  BS_CHECK_ARG(N >= 0 && K >= 1 && H >= 1 && W >= 1, "bad shape N=%d K=%d H=%d W=%d", N, K, H, W);
+  BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535, "shape too large");
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(scores_in && composed, "NULL pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return composite_dispatch(scores_in, composed, N, K, H, W, dtype, (cudaStream_t)stream);
+}
+
+int blobsplat_resize_bilinear(const void* in, void* out, int B, int Hin, int Win, int Hout, int Wout, int dtype,
+                              int device, void* stream) {
+  BS_CHECK_ARG(B >= 0 && Hin >= 1 && Win >= 1 && Hout >= 1 && Wout >= 1, "bad shape");
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  if (B == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(in && out, "NULL pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return resize_dispatch(in, out, B, Hin, Win, Hout, Wout, dtype, (cudaStream_t)stream);
+}
+
+int blobsplat_pyramid(const void* in, void* const* outs, int n_levels, int B, int S, int dtype, int device,
+                      void* stream) {
+  BS_CHECK_ARG(B >= 0 && S >= 1 && n_levels >= 1, "bad shape");
+  BS_CHECK_ARG(n_levels < 31 && (S % (1 << n_levels)) == 0, "S=%d is not divisible by 2^%d", S, n_levels);
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  if (B == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(in && outs, "NULL pointer");
+  for (int l = 0; l < n_levels; ++l) BS_CHECK_ARG(outs[l] != nullptr, "level %d output is NULL", l);
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return pyramid_dispatch(in, outs, n_levels, B, S, dtype, (cudaStream_t)stream);
+}
+
+int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride_k, int64_t stride_p,
+                            const void* features, void* out, int N, int K, int C, int H, int W, int dtype,
+                            int engine, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && K >= 1 && C >= 1 && H >= 1 && W >= 1, "bad shape N=%d K=%d C=%d H=%d W=%d", N, K, C, H, W);
+  BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535, "shape too large");
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TENSOR, "bad engine %d", engine);
+  BS_CHECK_ARG(stride_k >= 0 && stride_p >= 1 && stride_n >= 0, "bad strides");
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(scores && features && out, "NULL pointer");
+  if (engine == BLOBSPLAT_ENGINE_TENSOR)
+    BS_UNSUPPORTED("stand-alone stage 3 runs on the FMA engine; the tensor-core engine is the fused "
+                   "blobsplat_render (weights are produced on-chip as the TMEM operand)");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return feature_splat_fma_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
+                                    (cudaStream_t)stream);
+}
+
+int blobsplat_render(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,
+                     int feat_dtype, int N, int M, int H, int W, int C, void* composed, void* grid, int out_dtype,
+                     int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1 && C >= 1, "bad shape N=%d M=%d H=%d W=%d C=%d", N, M, H, W, C);
+  BS_CHECK_ARG((long long)H * W < (1ll << 31), "H*W must fit in int32");
+  BS_CHECK_ARG(valid_dtype(feat_dtype) && valid_dtype(out_dtype), "bad dtype");
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(xs && ys && covs && sizes && features && grid, "NULL pointer");
+  const char* why = nullptr;
+  if (!render_tc_supported(M + 1, C, H, W, feat_dtype, out_dtype, &why)) BS_UNSUPPORTED("fused render: %s", why);
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return render_tc_dispatch(xs, ys, covs, sizes, features, feat_dtype, N, M, H, W, C, composed, grid, out_dtype,
+                            (cudaStream_t)stream);
+}
+
+}  // extern "C"

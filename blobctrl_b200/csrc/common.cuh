@@ -1,0 +1,188 @@
+// Shared device/host helpers for the blob-splat kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/blobsplat.h"
+
+namespace blobsplat {
+
+// ---- error plumbing (thread-local message, C-ABI status codes) ----------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define BS_CHECK_ARG(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::blobsplat::set_error(__VA_ARGS__); \
+      return BLOBSPLAT_E_INVALID;          \
+    }                                      \
+  } while (0)
+
+#define BS_UNSUPPORTED(...)              \
+  do {                                   \
+    ::blobsplat::set_error(__VA_ARGS__); \
+    return BLOBSPLAT_E_UNSUPPORTED;      \
+  } while (0)
+
+#define BS_CUDA(call)                                                 \
+  do {                                                                \
+    cudaError_t _e = (call);                                          \
+    if (_e != cudaSuccess) return ::blobsplat::cuda_fail(_e, #call);  \
+  } while (0)
+
+// RAII device guard for the `device` argument of the C ABI.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int status = 0;
+  explicit DeviceGuard(int device) {
+    if (device < 0) return;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) { status = cuda_fail(e, "cudaGetDevice"); return; }
+    if (prev != device) {
+      e = cudaSetDevice(device);
+      if (e != cudaSuccess) { status = cuda_fail(e, "cudaSetDevice"); return; }
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+inline size_t dtype_size(int dt) {
+  switch (dt) {
+    case BLOBSPLAT_F32: return 4;
+    case BLOBSPLAT_F64: return 8;
+    case BLOBSPLAT_BF16: return 2;
+    case BLOBSPLAT_F16: return 2;
+    default: return 0;
+  }
+}
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// ---- scalar conversion -----------------------------------------------------------------------------
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+  __device__ __forceinline__ static float from(float v) { return v; }
+  __device__ __forceinline__ static float to(float v) { return v; }
+};
+template <> struct Cvt<double> {
+  __device__ __forceinline__ static double from(double v) { return v; }
+  __device__ __forceinline__ static double to(double v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  __device__ __forceinline__ static __nv_bfloat16 from(float v) { return __float2bfloat16_rn(v); }
+  __device__ __forceinline__ static float to(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+template <> struct Cvt<__half> {
+  __device__ __forceinline__ static __half from(float v) { return __float2half_rn(v); }
+  __device__ __forceinline__ static float to(__half v) { return __half2float(v); }
+};
+
+// ---- 128-bit (or narrower) vector stores of V consecutive elements, streaming (evict-first) --------
+// Outputs are written once and never re-read by the same kernel: st.global.cs keeps them from
+// displacing the small, hot inputs (blob table, features) in L1/L2.
+template <typename T, int V> struct VecStore;
+
+template <> struct VecStore<float, 4> {
+  __device__ __forceinline__ static void st(float* p, const float* v) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+};
+template <> struct VecStore<float, 1> {
+  __device__ __forceinline__ static void st(float* p, const float* v) { __stcs(p, v[0]); }
+};
+template <> struct VecStore<double, 2> {
+  __device__ __forceinline__ static void st(double* p, const double* v) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1]));
+  }
+};
+template <> struct VecStore<double, 1> {
+  __device__ __forceinline__ static void st(double* p, const double* v) { __stcs(p, v[0]); }
+};
+template <> struct VecStore<__nv_bfloat16, 8> {
+  __device__ __forceinline__ static void st(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    __stcs(reinterpret_cast<uint4*>(p), u);
+  }
+};
+template <> struct VecStore<__nv_bfloat16, 1> {
+  __device__ __forceinline__ static void st(__nv_bfloat16* p, const float* v) { *p = __float2bfloat16_rn(v[0]); }
+};
+template <> struct VecStore<__half, 8> {
+  __device__ __forceinline__ static void st(__half* p, const float* v) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    __stcs(reinterpret_cast<uint4*>(p), u);
+  }
+};
+template <> struct VecStore<__half, 1> {
+  __device__ __forceinline__ static void st(__half* p, const float* v) { *p = __float2half_rn(v[0]); }
+};
+
+// number of elements in one 128-bit store
+template <typename T> struct Vec128 { static constexpr int n = 16 / sizeof(T); };
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---- per-blob coefficients, built once per (image, blob) in fp64 and staged in shared memory -------
+// Whitened form: q*log2(e) = u^2 + v^2, u = p*dx, v = r*dx + t*dy, dx/dy in pixels
+// relative to the centre, which is kept as a hi+lo float pair so (x - cx) carries no fp32
+// cancellation error.  Non-positive-definite covariances (never produced by the reference's
+// callers) take the general quadratic form qa*dx^2 + qb*dx*dy + qc*dy^2 instead.
+struct __align__(16) BlobCoef {
+  float cx_hi, cx_lo, cy_hi, cy_lo;
+  float p, r, t;      // whitened (or qa, qb, qc when flags & kGeneral)
+  uint32_t flags;
+};
+constexpr uint32_t kGated = 1u;    // sizes < 0.5 -> score 1e-6  (utils.py:165-172)
+constexpr uint32_t kGeneral = 2u;  // covariance not PD: use the plain quadratic form
+
+__device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double c00, double c01, double c10,
+                                                   double c11, float size, int H, int W) {
+  BlobCoef o;
+  // centre in pixels: utils.py:138 (square) / :147 (tuple) — xs*W, ys*H
+  const double cx = xs * (double)W, cy = ys * (double)H;
+  o.cx_hi = (float)cx; o.cx_lo = (float)(cx - (double)o.cx_hi);
+  o.cy_hi = (float)cy; o.cy_lo = (float)(cy - (double)o.cy_hi);
+  // q = delta^T Sigma^-1 delta with delta = (dx/W, dy/H): only the symmetric part of Sigma^-1 matters.
+  const double det = c00 * c11 - c01 * c10;
+  const double l2e = 1.4426950408889634;
+  const double A = l2e * (c11 / det) / ((double)W * (double)W);
+  const double B = l2e * (-0.5 * (c01 + c10) / det) / ((double)W * (double)H);
+  const double C = l2e * (c00 / det) / ((double)H * (double)H);
+  o.flags = (size < 0.5f) ? kGated : 0u;
+  const double schur = A - (B * B) / C;
+  if (C > 0.0 && schur > 0.0) {
+    const double t = sqrt(C);
+    o.t = (float)t; o.r = (float)(B / t); o.p = (float)sqrt(schur);
+  } else {
+    o.p = (float)A; o.r = (float)(2.0 * B); o.t = (float)C;
+    o.flags |= kGeneral;
+  }
+  return o;
+}
+
+// s = min(1, 2*sigmoid(-q)) = min(1, 2 / (1 + 2^(q*log2e)))   (utils.py:162-163)
+__device__ __forceinline__ float opacity_from_q2(float q2) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q2));
+  return fminf(__fdividef(2.0f, 1.0f + e), 1.0f);
+}
+
+}  // namespace blobsplat

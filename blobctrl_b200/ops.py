@@ -1,0 +1,184 @@
+"""Tensor-level operators over the C ABI: allocate outputs with torch, pass raw pointers down.
+
+One function per C entry point (include/blobsplat.h).  The reference-signature layer
+(``blobctrl_b200.utils.utils``) is built from these.  CUDA tensors only — no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _capi as C
+
+_SELECT = {"all": C.SELECT_ALL, "fg": C.SELECT_FG, "bg": C.SELECT_BG}
+_MODE = {"auto": C.COMPOSITE_AUTO, "lane_pixel": C.COMPOSITE_LANE_PIXEL, "warp_scan": C.COMPOSITE_WARP_SCAN}
+_ENGINE = {"auto": C.ENGINE_AUTO, "fma": C.ENGINE_FMA, "tensor": C.ENGINE_TENSOR}
+
+_HALF = (torch.bfloat16, torch.float16)
+
+
+def canonical_blobs(xs, ys, covs, sizes) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, int, int]:
+    """Normalise the reference's accepted input shapes to dense [N,M] / [N,M,2,2] tensors.
+
+    utils.py:99-103 documents xs, ys [N,M], covs [N,M,2,2]; the reference's scripts pass xs, ys of
+    shape [1] with covs [1,1,2,2] (blobctrl_inference.py:101-109), which broadcasting treats as
+    [M] shared across the batch.  sizes may be [N,M] or [N,M,1] (utils.py:165-166).
+    Parameter dtype follows covs: float64 stays float64, everything else computes in float32.
+    """
+    C.require_cuda(covs, "covs")
+    if covs.ndim != 4 or covs.shape[-2:] != (2, 2):
+        raise RuntimeError(f"covs must be [N, M, 2, 2], got {tuple(covs.shape)}")
+    n, m = covs.shape[0], covs.shape[1]
+    pdt = torch.float64 if covs.dtype == torch.float64 else torch.float32
+    dev = covs.device
+
+    def centre(t, name):
+        t = torch.as_tensor(t, device=dev)
+        if t.ndim == 0:
+            t = t.reshape(1)
+        if t.ndim == 1:           # [M] (or [1]): shared across images
+            t = t.unsqueeze(0)
+        if t.ndim != 2:
+            raise RuntimeError(f"{name} must be [N, M], got {tuple(t.shape)}")
+        return t.to(pdt).expand(n, m).contiguous()
+
+    sizes = torch.as_tensor(sizes, device=dev)
+    if sizes.ndim == 3:
+        sizes = sizes.squeeze(-1)
+    if sizes.ndim == 1:
+        sizes = sizes.unsqueeze(0)
+    sizes = sizes.to(torch.float32).expand(n, m).contiguous()
+    return centre(xs, "xs"), centre(ys, "ys"), covs.to(pdt).contiguous(), sizes, n, m
+
+
+def render_scores(xs, ys, covs, sizes, height: int, width: int, select: str = "all", want_raw: bool = False,
+                  want_composed: bool = True, out_dtype: Optional[torch.dtype] = None,
+                  composite_mode: str = "auto") -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Stages 1+2 (blobsplat_scores).  Returns (composed [N,Ksel,H,W] | None, raw [N,K,H,W] | None)."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    if out_dtype is None:
+        out_dtype = covs.dtype if covs.dtype in (torch.float32, torch.float64) + _HALF else torch.float32
+    ksel = {"all": m + 1, "fg": m, "bg": 1}[select]
+    dev = covs_c.device
+    composed = torch.empty((n, ksel, height, width), dtype=out_dtype, device=dev) if want_composed else None
+    raw = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=dev) if want_raw else None
+    oc = C.dtype_code(out_dtype)
+    C.check(C.lib().blobsplat_scores(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.dtype_code(covs_c.dtype),
+                                     n, m, height, width, _SELECT[select], C.ptr(composed), oc, C.ptr(raw), oc,
+                                     _MODE[composite_mode], C.dev_of(covs_c), C.stream_of(covs_c)))
+    return composed, raw
+
+
+def composite(scores_nkhw: torch.Tensor) -> torch.Tensor:
+    """Stage 2 alone on planar raw scores [N,K,H,W] (blobsplat_composite)."""
+    C.require_cuda(scores_nkhw, "scores")
+    s = scores_nkhw.contiguous()
+    n, k, h, w = s.shape
+    out = torch.empty_like(s)
+    C.check(C.lib().blobsplat_composite(C.ptr(s), C.ptr(out), n, k, h, w, C.dtype_code(s.dtype), C.dev_of(s),
+                                        C.stream_of(s)))
+    return out
+
+
+def resize_bilinear(img: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
+    """[N,C,H,W] -> [N,C,out_h,out_w], align_corners=False (blobsplat_resize_bilinear)."""
+    C.require_cuda(img, "img")
+    x = img.contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device)
+    C.check(C.lib().blobsplat_resize_bilinear(C.ptr(x), C.ptr(out), n * c, h, w, out_h, out_w, C.dtype_code(x.dtype),
+                                              C.dev_of(x), C.stream_of(x)))
+    return out
+
+
+def halving_pyramid(img: torch.Tensor, cutoff: int) -> Dict[int, torch.Tensor]:
+    """utils.py:280-294 semantics; even square levels go through the one-launch pyramid kernel
+    (up to 3 levels per launch), anything else through the general bilinear resize."""
+    C.require_cuda(img, "img")
+    levels = [img]
+    cur = img
+    while cur.shape[-1] > cutoff:
+        n, c, h, w = cur.shape
+        # how many exact halvings can one launch do from here?
+        todo, s = 0, w
+        while h == w and s > cutoff and s % 2 == 0 and todo < 3:
+            s //= 2
+            todo += 1
+        if todo:
+            src = cur.contiguous()
+            outs = [torch.empty((n, c, w >> (l + 1), w >> (l + 1)), dtype=cur.dtype, device=cur.device)
+                    for l in range(todo)]
+            arr = (ctypes.c_void_p * todo)(*[o.data_ptr() for o in outs])
+            C.check(C.lib().blobsplat_pyramid(C.ptr(src), arr, todo, n * c, w, C.dtype_code(cur.dtype),
+                                              C.dev_of(cur), C.stream_of(cur)))
+            levels.extend(outs)
+            cur = outs[-1]
+        else:
+            cur = resize_bilinear(cur, w // 2, w // 2)
+            levels.append(cur)
+    return {int(t.size(-1)): t for t in levels}
+
+
+def _linear_pixel_strides(s: torch.Tensor):
+    """(stride_n, stride_k, stride_p) of a logical [N,K,H,W] view whose pixel index p = y*W + x is
+    linear in memory, else None (the caller then materialises a contiguous copy)."""
+    _, _, h, w = s.shape
+    sn, sk, sh, sw = s.stride()
+    if w == 1:
+        sp = sh if h > 1 else 1
+    elif h == 1 or sh == w * sw:
+        sp = sw
+    else:
+        return None
+    if sp < 1 or sk < 0 or sn < 0:
+        return None
+    return sn, sk, sp
+
+
+def feature_splat(scores: torch.Tensor, features: torch.Tensor, channels_last: bool = False,
+                  engine: str = "auto") -> torch.Tensor:
+    """Stage 3 (blobsplat_feature_splat): scores [N,K,H,W] (or [N,H,W,K]) x features [N,K,C] -> [N,C,H,W].
+    Strided score views are consumed in place when their pixel index is linear (no copy)."""
+    C.require_cuda(scores, "scores")
+    if scores.ndim != 4 or features.ndim != 3:
+        raise RuntimeError(f"scores must be 4-D and features 3-D, got {tuple(scores.shape)} / {tuple(features.shape)}")
+    s = scores.permute(0, 3, 1, 2) if channels_last else scores        # logical [N,K,H,W]
+    n, k, h, w = s.shape
+    if features.shape[0] != n or features.shape[1] != k:
+        raise RuntimeError(f"einsum(): operands do not broadcast: scores {tuple(s.shape)} (N,K,H,W) vs features "
+                           f"{tuple(features.shape)} (N,K,C)")
+    f = features.to(dtype=s.dtype, device=s.device).contiguous()        # utils.py:69
+    strides = _linear_pixel_strides(s)
+    if strides is None:
+        s = s.contiguous()
+        strides = _linear_pixel_strides(s)
+    sn, sk, sp = strides
+    c = f.shape[2]
+    out = torch.empty((n, c, h, w), dtype=s.dtype, device=s.device)
+    C.check(C.lib().blobsplat_feature_splat(C.ptr(s), sn, sk, sp, C.ptr(f), C.ptr(out), n, k, c, h, w,
+                                            C.dtype_code(s.dtype), _ENGINE[engine], C.dev_of(s), C.stream_of(s)))
+    return out
+
+
+def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width: int,
+                 out_dtype: Optional[torch.dtype] = None, want_composed: bool = True):
+    """Stages 1+2+3 in one launch (blobsplat_render, tcgen05).  Returns (composed | None, grid).
+    Raises BlobSplatError when the shape is outside the tensor-core kernel's envelope."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    if covs_c.dtype != torch.float32:
+        raise C.BlobSplatError("blobsplat: unsupported: fused render takes float32 blob parameters")
+    if out_dtype is None:
+        out_dtype = features.dtype
+    f = features.to(device=covs_c.device).contiguous()
+    if f.ndim != 3 or f.shape[0] != n or f.shape[1] != m + 1:
+        raise RuntimeError(f"features must be [N, M+1, C] = [{n}, {m + 1}, C], got {tuple(f.shape)}")
+    c = f.shape[2]
+    dev = covs_c.device
+    composed = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=dev) if want_composed else None
+    grid = torch.empty((n, c, height, width), dtype=out_dtype, device=dev)
+    C.check(C.lib().blobsplat_render(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.ptr(f),
+                                     C.dtype_code(f.dtype), n, m, height, width, c, C.ptr(composed), C.ptr(grid),
+                                     C.dtype_code(out_dtype), C.dev_of(covs_c), C.stream_of(covs_c)))
+    return composed, grid

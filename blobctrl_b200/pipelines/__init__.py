@@ -1,0 +1,5 @@
+from .conditioning import (BlobConditioning, BlobConditioningMixin, construct_blobnet_input,
+                           prepare_blob_conditioning, splat_features_from_scores)
+
+__all__ = ["BlobConditioning", "BlobConditioningMixin", "construct_blobnet_input", "prepare_blob_conditioning",
+           "splat_features_from_scores"]

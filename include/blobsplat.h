@@ -1,0 +1,164 @@
+/*
+ * blobsplat.h — C ABI of the B200-native (sm_100a) blob-splat library.
+ *
+ * This is the drop-in boundary for ONE hot path of TencentARC/BlobCtrl: the BlobGAN-style blob
+ * renderer in blobctrl/utils/utils.py.  The reference has no FFI of its own (it is pure Python over
+ * ATen), so each entry point below cites the reference Python interface (file:line, relative to the
+ * reference tree) whose arithmetic it replaces.  The host side that keeps the reference's Python
+ * signatures lives in blobctrl_b200/ and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise.
+ *   - The caller owns and allocates every buffer; the library never allocates, frees or retains
+ *     device memory, keeps no mutable global state and is re-entrant.
+ *   - All work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream).  No host synchronisation, no allocation: every call is CUDA-graph
+ *     capturable.
+ *   - `device` is the CUDA ordinal that owns the buffers, or -1 for "the calling thread's current
+ *     device".  When >= 0 the library makes it current for the duration of the call and restores
+ *     the previous one.
+ *   - Every function returns 0 on success or a negative blobsplat_status; the message is available
+ *     per thread through blobsplat_last_error().  There is NO CPU fallback: unsupported
+ *     combinations fail with BLOBSPLAT_E_UNSUPPORTED.
+ *   - Tensors are dense row-major in the shapes given; K = M + 1 (channel 0 = background).
+ */
+#ifndef BLOBSPLAT_H_
+#define BLOBSPLAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLOBSPLAT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define BLOBSPLAT_API __attribute__((visibility("default")))
+#else
+#define BLOBSPLAT_API
+#endif
+
+typedef enum {
+  BLOBSPLAT_OK = 0,
+  BLOBSPLAT_E_INVALID = -1,      /* bad shape / null pointer / misaligned buffer / bad enum */
+  BLOBSPLAT_E_UNSUPPORTED = -2,  /* valid request this build cannot run (dtype combo, K or C limits) */
+  BLOBSPLAT_E_CUDA = -3          /* a CUDA runtime call failed; message carries cudaGetErrorString */
+} blobsplat_status;
+
+typedef enum {
+  BLOBSPLAT_F32 = 0,
+  BLOBSPLAT_F64 = 1,
+  BLOBSPLAT_BF16 = 2,
+  BLOBSPLAT_F16 = 3
+} blobsplat_dtype;
+
+/* utils.py:183-191 — only_splatting_bg / only_splatting_fg */
+typedef enum {
+  BLOBSPLAT_SELECT_ALL = 0, /* channels 0..M   -> K planes  */
+  BLOBSPLAT_SELECT_FG = 1,  /* channels 1..M   -> M planes  */
+  BLOBSPLAT_SELECT_BG = 2   /* channel 0 only  -> 1 plane   */
+} blobsplat_select;
+
+/* Stage-2 thread mapping (both are measured; AUTO picks by shape) */
+typedef enum {
+  BLOBSPLAT_COMPOSITE_AUTO = 0,
+  BLOBSPLAT_COMPOSITE_LANE_PIXEL = 1, /* one thread walks k = M..0 with the transmittance in a register */
+  BLOBSPLAT_COMPOSITE_WARP_SCAN = 2   /* lane = blob; multiplicative suffix scan with warp shuffles */
+} blobsplat_composite_mode;
+
+/* Stage-3 engine */
+typedef enum {
+  BLOBSPLAT_ENGINE_AUTO = 0,
+  BLOBSPLAT_ENGINE_FMA = 1,    /* CUDA-core FP32/FP64 FMA tiles */
+  BLOBSPLAT_ENGINE_TENSOR = 2  /* tcgen05 MMA (bf16/f16: kind::f16; f32: 3xTF32 split) */
+} blobsplat_engine;
+
+typedef struct {
+  int abi_version;
+  int sm_arch;            /* 100 */
+  int max_blobs;          /* largest M accepted by blobsplat_scores */
+  int tensor_max_k;       /* largest K = M+1 the tensor-core render accepts */
+  int tensor_c_multiple;  /* C must be a multiple of this for the tensor-core render */
+  int tensor_max_c;       /* largest C the tensor-core render accepts */
+} blobsplat_caps;
+
+BLOBSPLAT_API int blobsplat_abi_version(void);
+BLOBSPLAT_API int blobsplat_get_caps(blobsplat_caps* out);
+/* copies the calling thread's last error message (NUL-terminated) into buf; returns its length */
+BLOBSPLAT_API int blobsplat_last_error(char* buf, size_t cap);
+
+/*
+ * (1) scores — stages 1+2.  Replaces utils.py:120-194 (splat_features up to `return_d_score`):
+ *     delta = (pixel - centre*size)/size, q = delta^T Sigma^-1 delta, s = min(1, 2*sigmoid(-q)),
+ *     sizes < 0.5 -> 1e-6, background alpha 1 prepended, d_k = s_k * prod_{j>k}(1 - s_j), d_M = s_M.
+ *
+ *   xs, ys   [N, M]        blob centres in [0,1] (fractions of W, H)
+ *   covs     [N, M, 2, 2]  covariances, normalised by the image diagonal^2
+ *   sizes    [N, M]        float32 existence flags (the reference compares `< 0.5`)
+ *   param_dtype            BLOBSPLAT_F32 or BLOBSPLAT_F64 (dtype of xs/ys/covs; also the compute type)
+ *   composed [N, Ksel, H, W] (Ksel = K, M or 1 by `select`), dtype composed_dtype; may be NULL
+ *   raw      [N, K, H, W]  raw scores incl. the background plane of ones, dtype raw_dtype; may be NULL
+ *            (the reference's layout dict holds them as [N,H,W,K]; the host wrapper returns a
+ *             permuted view of this planar buffer — same shape and values)
+ *   Output dtypes: F32/BF16/F16 when param_dtype is F32; F64 when param_dtype is F64.
+ */
+BLOBSPLAT_API int blobsplat_scores(const void* xs, const void* ys, const void* covs, const float* sizes,
+                     int param_dtype, int N, int M, int H, int W, int select,
+                     void* composed, int composed_dtype, void* raw, int raw_dtype,
+                     int composite_mode, int device, void* stream);
+
+/*
+ * (1b) composite only.  Replaces utils.py:179-181 / :205-206 applied to caller-modified raw scores
+ *      (the `viz_score_fn` branch).  scores_in / composed: planar [N, K, H, W], same dtype.
+ */
+BLOBSPLAT_API int blobsplat_composite(const void* scores_in, void* composed, int N, int K, int H, int W,
+                        int dtype, int device, void* stream);
+
+/*
+ * (2) bilinear resize, align_corners = False.  Replaces torch.nn.functional.interpolate(mode=
+ *     'bilinear') as used by pyramid_resize (utils.py:280-294) and by splat_features_from_scores
+ *     (utils.py:70-73).  in [B, Hin, Win] -> out [B, Hout, Wout], same dtype.
+ */
+BLOBSPLAT_API int blobsplat_resize_bilinear(const void* in, void* out, int B, int Hin, int Win, int Hout, int Wout,
+                              int dtype, int device, void* stream);
+
+/*
+ * (2b) whole pyramid in one launch: in [B, S, S] -> levels S/2, S/4, ... (n_levels of them), each an
+ *      exact 2x2 mean of the previous (== the reference's bilinear halving for even sizes, SURVEY
+ *      probe B7).  outs: HOST array of n_levels device pointers.  S must be divisible by 2^n_levels.
+ */
+BLOBSPLAT_API int blobsplat_pyramid(const void* in, void* const* outs, int n_levels, int B, int S, int dtype,
+                      int device, void* stream);
+
+/*
+ * (3) feature splat — stage 3.  Replaces splat_features_from_scores (utils.py:57-77) and the
+ *     duplicate pipeline method (pipelines/pipeline_blobnet.py:706-721) after the optional resize:
+ *         out[n, c, y, x] = sum_k scores[n, k, y, x] * features[n, k, c]      (NCHW, contiguous)
+ *   scores: element strides (in elements) stride_n, stride_k, stride_p with pixel p = y*W + x
+ *           ([N,K,H,W] contiguous: K*P, P, 1;  [N,H,W,K] contiguous: P*K, 1, K)
+ *   features [N, K, C] contiguous, same dtype as scores and out.
+ */
+BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride_k, int64_t stride_p,
+                            const void* features, void* out, int N, int K, int C, int H, int W,
+                            int dtype, int engine, int device, void* stream);
+
+/*
+ * (4) fused render — stages 1+2+3 in ONE launch: blob parameters + features -> composed score maps
+ *     and the feature grid at the same resolution, with the per-pixel weights never leaving the SM
+ *     (tcgen05 MMA with the weights as the TMEM A operand).  Replaces the whole of splat_features
+ *     (utils.py:80-241) for interp_size == score_size.
+ *   features [N, K, C] (dtype feat_dtype: F32, BF16 or F16); grid [N, C, H, W] (dtype out_dtype);
+ *   composed [N, K, H, W] (dtype out_dtype) or NULL.  param dtype is F32.
+ *   F32 out: 3xTF32 split-precision MMA (error ~2^-21, inside the 1e-5 parity bar);
+ *   BF16/F16 out: single kind::f16 MMA with fp32 accumulation.
+ */
+BLOBSPLAT_API int blobsplat_render(const float* xs, const float* ys, const float* covs, const float* sizes,
+                     const void* features, int feat_dtype, int N, int M, int H, int W, int C,
+                     void* composed, void* grid, int out_dtype, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLOBSPLAT_H_ */

@@ -1,0 +1,317 @@
+"""GPU parity: the CUDA path (through the reference-signature API -> ctypes -> C ABI) against
+(a) the golden fixtures recorded from the real reference and (b) the float64 numpy oracle on seeded
+inputs, plus size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.json north_star; SURVEY.md §7.2 for the scale-relative definition):
+  fp32 maps : |got - ref| <= 1e-5 * max|ref| (+1e-5 elementwise-relative)   [scores live in [0,1]]
+  bf16 maps : |got - ref| <= 1e-2 * max|ref|
+  fp64 maps : 1e-9 relative
+  ordering / indexing (argmax_k, channel order, fg/bg selection): exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as G
+from oracle import blob_oracle
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _impl():
+    import blobctrl_b200.utils.utils as U
+    return U
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def _np(t):
+    return t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.detach().cpu().numpy()
+
+
+def _blob(syn, dtype=torch.float32):
+    return {k: (_cuda(v).to(dtype) if k != "sizes" else _cuda(v)) for k, v in syn.items() if k != "features"}
+
+
+def close_scaled(got, want, rel, what):
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{what}: {got.shape} vs {want.shape}"
+    scale = max(float(np.abs(want).max()), 1e-30)
+    err = np.abs(got - want)
+    assert np.isfinite(got).all(), f"{what}: non-finite output"
+    assert err.max() <= rel * scale, f"{what}: max abs err {err.max():.3e} > {rel:g} * {scale:.3g}"
+
+
+CASES = G.cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_cases(case):
+    U = _impl()
+    f64 = not case["name"].endswith("_f32") and any(
+        G.arrays()[f"{case['name']}/out/{k}"].dtype == np.float64 for k in case["outs"])
+    for key, got, want in G.run_case(case, U, wrap=_cuda, to_np=_np, identity_fn=U.viz_score_fn):
+        if key == "feature_img_moments":
+            G.check_close(got, want, 1e-9 if f64 else 3e-5, 0, f"{case['name']}:{key}")
+            continue
+        assert got.dtype == want.dtype, (key, got.dtype, want.dtype)
+        # thin blobs in fp32: the reference's own LU solve is 6.7e-6 abs / 5e-3 rel from its fp64 self
+        rel = 1e-9 if f64 else (2e-5 if case["name"].startswith("thin") else 1e-5)
+        close_scaled(got, want, rel, f"{case['name']}:{key}")
+
+
+def test_forty_demo_ellipses_fp64_script_recipe():
+    """scripts/blobctrl_inference.py:71-117 on all 40 state.json ellipses, float64 like the scripts."""
+    U = _impl()
+    want = G.arrays()["ellipses/fg64"]
+    for i, e in enumerate(G.ellipses()):
+        mean, cov = U.get_gs_from_ellipse(e["ellipse"])
+        nm, nc = U.normalize_gs(mean, cov, 512, 512)
+        blob = U.get_blob_dict_from_norm_gs(nm, nc, device=DEV)
+        score = U.get_blob_score_from_blob_dict(blob, score_size=(64, 64))
+        assert score.shape == (2, 64, 64) and score.dtype == torch.float64
+        got = score.cpu().numpy()
+        close_scaled(got[1], want[i], 1e-9, f"{e['demo']}[{e['idx']}] fg")
+        close_scaled(got[0], 1 - want[i], 1e-9, f"{e['demo']}[{e['idx']}] bg")
+        # same ellipse with float32 tensors: 1e-5 of scale against the float64 reference
+        b32 = {k: (v.float()) for k, v in blob.items()}
+        got32 = U.get_blob_score_from_blob_dict(b32, score_size=(64, 64)).cpu().numpy()
+        assert got32.dtype == np.float32
+        if e["ellipse"][1] != [1e-05, 1e-05]:
+            close_scaled(got32[1], want[i], 1e-5, f"{e['demo']}[{e['idx']}] fg fp32")
+        else:                                   # degenerate: exactly one pixel at 1.0, rest 0
+            assert (got32[1] == 1.0).sum() == 1 and (got32[1] > 0).sum() == 1
+            assert np.array_equal(got32[1] > 0, want[i] > 0)
+
+
+@pytest.mark.parametrize("n,m,s,c,seed", [(1, 16, 64, 320, 1), (3, 32, 64, 320, 2), (2, 64, 64, 64, 3), (2, 5, 40, 33, 4)])
+def test_synthetic_vs_fp64_oracle_fp32(n, m, s, c, seed):
+    """BASELINE config 2 (16 blobs x 64x64 x 320ch) and neighbours, full dict, fp32 vs the fp64 oracle."""
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(n, m, seed=seed, c=c)
+    want = blob_oracle.splat_features(**syn, score_size=s, interp_size=s, dtype=np.float64)
+    for engine in ("fma", "auto"):
+        got = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=s, interp_size=s,
+                               engine=engine)
+        assert set(got) == set(want)
+        assert got["feature_img"] is None and got["entropy_img"] is None
+        close_scaled(_np(got["scores_pyramid"][s]), want["scores_pyramid"][s], 1e-5, "composed")
+        close_scaled(_np(got["composed_scores"]), want["composed_scores"], 1e-5, "composed NHWK view")
+        close_scaled(_np(got["raw_scores"]), want["raw_scores"], 1e-5, "raw")
+        close_scaled(_np(got["feature_grid"]), want["feature_grid"], 1e-5, "feature grid")
+        assert got["feature_grid"].is_contiguous() and got["feature_grid"].shape == (n, c, s, s)
+        # ordering / indexing exact: front-most blob per pixel agrees wherever the oracle's margin is real
+        d = want["scores_pyramid"][s]
+        top2 = np.sort(d, axis=1)[:, -2:]
+        sure = (top2[:, 1] - top2[:, 0]) > 1e-5
+        assert np.array_equal(_np(got["scores_pyramid"][s]).argmax(1)[sure], d.argmax(1)[sure])
+        no_layout = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=s, interp_size=s,
+                                     ret_layout=False, engine=engine)
+        assert "raw_scores" not in no_layout
+        close_scaled(_np(no_layout["feature_grid"]), want["feature_grid"], 1e-5, "feature grid (no layout)")
+        close_scaled(_np(no_layout["scores_pyramid"][s]), want["scores_pyramid"][s], 1e-5, "composed (no layout)")
+
+
+def test_thin_blobs_closer_to_fp64_than_reference_fp32():
+    """Whitened quadratic form: on thin blobs the CUDA fp32 result is nearer the fp64 reference than the
+    reference's own fp32 run (golden 'thin_f32' vs 'thin_f64')."""
+    U = _impl()
+    z = G.arrays()
+    ins = {k: _cuda(z[f"thin_f32/in/{k}"]) for k in ("xs", "ys", "covs", "sizes")}
+    got = _np(U.splat_features(**ins, score_size=32, return_d_score=True))
+    ref64 = blob_oracle.splat_features(**{k: z[f"thin_f32/in/{k}"] for k in ("xs", "ys", "covs", "sizes")},
+                                       score_size=32, return_d_score=True, dtype=np.float64)
+    ours = np.abs(got - ref64).max()
+    theirs = np.abs(z["thin_f32/out/ret"].astype(np.float64) - ref64).max()
+    assert ours <= 1e-5 and ours <= theirs * 1.5 + 1e-7, (ours, theirs)
+
+
+@pytest.mark.parametrize("dtype,rel", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+def test_multiscale_config3_half(dtype, rel):
+    """BASELINE config 3 at reduced batch: 32 blobs, levels 64/32/16/8, C = 320/640/1280/1280, 16-bit maps."""
+    U = _impl()
+    n, m = 2, 32
+    syn = blob_oracle.synthetic_blobs(n, m, seed=1)
+    rng = np.random.default_rng(11)
+    chans = {64: 320, 32: 640, 16: 1280, 8: 1280}
+    feats = {s: rng.standard_normal((n, m + 1, c)).astype(np.float32) for s, c in chans.items()}
+    d = blob_oracle.render_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], 64, 64, np.float64)
+    pyr = blob_oracle.pyramid_resize(d, 8)
+    got = U.splat_features_multiscale(**_blob(syn), score_size=64,
+                                      level_features={s: _cuda(f).to(dtype) for s, f in feats.items()},
+                                      out_dtype=dtype)
+    assert sorted(got["scores_pyramid"]) == [8, 16, 32, 64]
+    for s, c in chans.items():
+        assert got["scores_pyramid"][s].dtype == dtype and got["feature_grids"][s].shape == (n, c, s, s)
+        close_scaled(_np(got["scores_pyramid"][s]), pyr[s], rel, f"scores@{s}")
+        f_q = _np(_cuda(feats[s]).to(dtype)).astype(np.float64)          # features as the kernel sees them
+        want = blob_oracle.splat_features_from_scores(pyr[s], f_q, s, channels_last=False)
+        close_scaled(_np(got["feature_grids"][s]), want, rel, f"grid@{s}")
+
+
+def test_multiscale_fp32():
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, 32, seed=2)
+    rng = np.random.default_rng(12)
+    feats = {64: rng.standard_normal((2, 33, 64)).astype(np.float32), 16: rng.standard_normal((2, 33, 48)).astype(np.float32)}
+    d = blob_oracle.render_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], 64, 64, np.float64)
+    pyr = blob_oracle.pyramid_resize(d, 16)
+    got = U.splat_features_multiscale(**_blob(syn), score_size=64, level_features={s: _cuda(f) for s, f in feats.items()})
+    for s in (64, 32, 16):
+        close_scaled(_np(got["scores_pyramid"][s]), pyr[s], 1e-5, f"scores@{s}")
+    for s, f in feats.items():
+        want = blob_oracle.splat_features_from_scores(pyr[s], f.astype(np.float64), s, channels_last=False)
+        close_scaled(_np(got["feature_grids"][s]), want, 1e-5, f"grid@{s}")
+
+
+@pytest.mark.parametrize("m", [1, 31, 32, 33, 64, 100])
+def test_warp_scan_matches_lane_pixel(m):
+    """The two stage-2 mappings agree to a few ulp (scan re-association), and both match the oracle."""
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, m, seed=5)
+    b = _blob(syn)
+    a = U.splat_features(**b, score_size=48, return_d_score=True, composite_mode="lane_pixel")
+    w = U.splat_features(**b, score_size=48, return_d_score=True, composite_mode="warp_scan")
+    want = blob_oracle.render_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], 48, 48, np.float64)
+    close_scaled(_np(a), want, 1e-5, "lane_pixel")
+    close_scaled(_np(w), want, 1e-5, "warp_scan")
+    assert (a - w).abs().max().item() <= 2e-6
+    for sel in ("only_splatting_fg", "only_splatting_bg"):
+        ws = U.splat_features(**b, score_size=48, return_d_score=True, composite_mode="warp_scan", **{sel: True})
+        ls = U.splat_features(**b, score_size=48, return_d_score=True, **{sel: True})
+        assert ws.shape == ls.shape and (ws - ls).abs().max().item() <= 2e-6
+
+
+def test_selection_and_layout_exact():
+    """fg drops channel 0, bg keeps only channel 0 as [N,1,H,W]; channel k is blob k-1 — bit-exact slices."""
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(3, 7, seed=6)
+    b = _blob(syn)
+    full = U.splat_features(**b, score_size=20, return_d_score=True)
+    fg = U.splat_features(**b, score_size=20, return_d_score=True, only_splatting_fg=True)
+    bg = U.splat_features(**b, score_size=20, return_d_score=True, only_splatting_bg=True)
+    assert full.shape == (3, 8, 20, 20) and fg.shape == (3, 7, 20, 20) and bg.shape == (3, 1, 20, 20)
+    assert torch.equal(fg, full[:, 1:]) and torch.equal(bg, full[:, :1])
+    # front-most = highest index: a lone opaque blob in the last slot hides everything beneath its centre
+    assert torch.allclose(full.sum(1), torch.ones_like(full[:, 0]), atol=2e-6)   # partition of unity
+
+
+def test_large_m_chunking_and_odd_sizes():
+    """M > the 128-blob shared-memory chunk, W not a multiple of the vector width, tiny images."""
+    U = _impl()
+    for (n, m, h) in [(1, 300, 17), (2, 129, 6), (1, 2, 1)]:
+        syn = blob_oracle.synthetic_blobs(n, m, seed=7)
+        got = U.splat_features(**_blob(syn), score_size=h, return_d_score=True)
+        want = blob_oracle.render_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], h, h, np.float64)
+        close_scaled(_np(got), want, 1e-5, f"M={m} S={h}")
+
+
+def test_full_size_properties_config5():
+    """BASELINE config 5 at full size on one GPU (1024 images x 64 blobs, 64x64, C=320, fp32): properties
+    that do not need the oracle — partition of unity, linearity of stage 3 in the features, constant
+    features reproduce themselves — plus a 4-image slice against the fp64 oracle."""
+    U = _impl()
+    n, m, s, c = 1024, 64, 64, 320
+    syn = blob_oracle.synthetic_blobs(n, m, seed=0, c=c)
+    b = _blob(syn)
+    f = _cuda(syn["features"])
+    out = U.splat_features(**b, features=f, score_size=s, interp_size=s, ret_layout=False)
+    d, g = out["scores_pyramid"][s], out["feature_grid"]
+    assert d.shape == (n, m + 1, s, s) and g.shape == (n, c, s, s)
+    assert (d.sum(1) - 1).abs().max().item() <= 4e-6                       # sum_k d_k = 1
+    assert d.min().item() >= 0 and d.max().item() <= 1
+    ones = U.splat_features_from_scores(d, torch.ones(n, m + 1, 8, device=DEV), s, channels_last=False)
+    assert (ones - 1).abs().max().item() <= 4e-6                           # constant features -> constant map
+    f2 = torch.randn_like(f)
+    lin = U.splat_features_from_scores(d[:64], (2 * f + 3 * f2)[:64], s, channels_last=False)
+    sep = 2 * U.splat_features_from_scores(d[:64], f[:64], s, channels_last=False) + \
+        3 * U.splat_features_from_scores(d[:64], f2[:64], s, channels_last=False)
+    assert (lin - sep).abs().max().item() <= 1e-4 * float(lin.abs().max())   # linearity
+    sl = slice(509, 513)
+    want = blob_oracle.splat_features(**{k: v[sl] for k, v in syn.items()}, score_size=s, interp_size=s,
+                                      dtype=np.float64, ret_layout=False)
+    close_scaled(_np(d[sl]), want["scores_pyramid"][s], 1e-5, "cfg5 composed slice")
+    close_scaled(_np(g[sl]), want["feature_grid"], 1e-5, "cfg5 grid slice")
+
+
+def test_pipeline_conditioning_entry():
+    """pipeline_blobnet.py:973-984 + :724-739: K=1, C=1024, fp16, layouts [2B,1029,64,128] / [2B,5,64,128]."""
+    from blobctrl_b200.pipelines import construct_blobnet_input, prepare_blob_conditioning
+    U = _impl()
+    e = G.ellipses()[20]["ellipse"]
+    nm, nc = U.normalize_gs(*U.get_gs_from_ellipse(e), 512, 512)
+    gs = U.get_blob_score_from_blob_dict(U.get_blob_dict_from_norm_gs(nm, nc, device="cuda"), (64, 64)).unsqueeze(0)
+    g = torch.Generator(device="cpu").manual_seed(3)
+    dino = torch.randn(1, 1, 1024, generator=g).to(DEV)
+    cond = prepare_blob_conditioning(gs, dino, batch=4, dtype=torch.float16, device=DEV)
+    assert cond.fg_gs_feats.shape == (4, 1024, 64, 64) and cond.fg_gs_feats.dtype == torch.float16
+    want = (gs[:, 1:2].half().float()[:, :, None] * dino.half().float()[:, 0, :, None, None, None]).squeeze(3)
+    want = want.reshape(1, 1024, 64, 64).expand(4, -1, -1, -1)
+    assert (cond.fg_gs_feats.float() - want).abs().max().item() <= 1e-2 * float(want.abs().max())
+    lat = torch.randn(4, 4, 64, 64, device=DEV, dtype=torch.float16)
+    img = torch.randn(4, 4, 64, 64, device=DEV, dtype=torch.float16)
+    x = construct_blobnet_input(lat, cond.fg_gs_scores, img, cond.fg_gs_feats)
+    assert x.shape == (4, 1029, 64, 128)
+    assert torch.equal(x[:, :4, :, :64], img) and torch.equal(x[:, :4, :, 64:], lat)
+    assert torch.equal(x[:, 4:5, :, :64], cond.fg_gs_scores) and torch.equal(x[:, 5:, :, 64:], cond.fg_gs_feats)
+    xb = construct_blobnet_input(lat, cond.bg_gs_scores, img, background=True)
+    assert xb.shape == (4, 5, 64, 128)
+
+
+def test_errors_and_no_cpu_fallback():
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, 3, seed=9, c=4)
+    cpu = {k: torch.from_numpy(v) for k, v in syn.items() if k != "features"}
+    with pytest.raises(RuntimeError, match="no CPU"):
+        U.splat_features(**cpu, score_size=8, return_d_score=True)
+    b = _blob(syn)
+    with pytest.raises(RuntimeError):                       # tuple size with N*M > 1 (utils.py:157-159)
+        U.splat_features(**b, score_size=(8, 8), return_d_score=True)
+    with pytest.raises(TypeError):                          # interp_size missing (utils.py:291)
+        U.splat_features(**b, score_size=8, features=_cuda(syn["features"]))
+    with pytest.raises(KeyError):                           # interp_size not a pyramid level
+        U.splat_features(**b, score_size=8, interp_size=16, features=_cuda(syn["features"]))
+    with pytest.raises(RuntimeError):                       # feature rows != channels
+        U.splat_features(**b, score_size=8, interp_size=8, features=_cuda(syn["features"])[:, :2])
+    from blobctrl_b200 import _capi
+    with pytest.raises(_capi.BlobSplatError):               # warp-scan limit
+        big = blob_oracle.synthetic_blobs(1, 300, seed=1)
+        U.splat_features(**_blob(big), score_size=8, return_d_score=True, composite_mode="warp_scan")
+
+
+def test_cuda_graph_capture_and_streams():
+    """The C ABI neither allocates nor synchronises: a render can be captured and replayed."""
+    from blobctrl_b200 import ops
+    syn = blob_oracle.synthetic_blobs(2, 16, seed=10, c=32)
+    b = _blob(syn); f = _cuda(syn["features"])
+    xs, ys, covs, sizes, n, m = ops.canonical_blobs(**b)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        ref_d, _ = ops.render_scores(xs, ys, covs, sizes, 32, 32)
+        ref_g = ops.feature_splat(ref_d, f)
+    side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        d, _ = ops.render_scores(xs, ys, covs, sizes, 32, 32)
+        g = ops.feature_splat(d, f)
+    d.zero_(); g.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(d, ref_d) and torch.equal(g, ref_g)
+
+
+def test_custom_viz_score_fn_branch():
+    """utils.py:199-209: a non-identity viz_score_fn re-composites the modified raw scores."""
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, 6, seed=12)
+    fn_t = lambda s: torch.cat([s[..., :1], (s[..., 1:] * 1.5).clamp(max=1)], -1)
+    fn_n = lambda s: np.concatenate([s[..., :1], np.minimum(s[..., 1:] * 1.5, 1)], -1)
+    got = U.splat_features(**_blob(syn), score_size=16, interp_size=16, viz_size=16, is_viz=True, only_vis=True,
+                           viz_score_fn=fn_t, viz_colors=U.BLOB_VIS_COLORS)
+    want = blob_oracle.splat_features(**syn, score_size=16, interp_size=16, viz_size=16, is_viz=True, only_vis=True,
+                                      viz_score_fn=fn_n, viz_colors=blob_oracle.BLOB_VIS_COLORS, dtype=np.float64)
+    close_scaled(_np(got["feature_img"]), want["feature_img"], 1e-5, "custom viz")
