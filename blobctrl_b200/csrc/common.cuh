@@ -5,8 +5,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <type_traits>
 
 #include "../../include/blobsplat.h"
 
@@ -183,6 +185,19 @@ __device__ __forceinline__ float opacity_from_q2(float q2) {
   float e;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q2));
   return fminf(__fdividef(2.0f, 1.0f + e), 1.0f);
+}
+
+// raw opacity of one blob at one pixel (stage 1 + gate)
+__device__ __forceinline__ float blob_opacity(const BlobCoef& c, float xf, float yf) {
+  if (c.flags & kGated) return 1e-6f;
+  const float dy = (yf - c.cy_hi) - c.cy_lo;
+  const float dx = (xf - c.cx_hi) - c.cx_lo;
+  if (!(c.flags & kGeneral)) {
+    const float u = c.p * dx;
+    const float v = fmaf(c.r, dx, c.t * dy);
+    return opacity_from_q2(fmaf(u, u, v * v));
+  }
+  return opacity_from_q2(fmaf(dx, fmaf(c.p, dx, c.r * dy), c.t * dy * dy));
 }
 
 }  // namespace blobsplat

@@ -189,18 +189,6 @@ constexpr int kScanWarps = 4;
 constexpr int kScanMaxBlobs = 256;
 constexpr int kTileStride = 33;  // [K][32] tile padded to 33 floats: conflict-free column writes
 
-__device__ __forceinline__ float blob_opacity(const BlobCoef& c, float xf, float yf) {
-  if (c.flags & kGated) return 1e-6f;
-  const float dy = (yf - c.cy_hi) - c.cy_lo;
-  const float dx = (xf - c.cx_hi) - c.cx_lo;
-  if (!(c.flags & kGeneral)) {
-    const float u = c.p * dx;
-    const float v = fmaf(c.r, dx, c.t * dy);
-    return opacity_from_q2(fmaf(u, u, v * v));
-  }
-  return opacity_from_q2(fmaf(dx, fmaf(c.p, dx, c.r * dy), c.t * dy * dy));
-}
-
 template <typename O>
 __global__ void __launch_bounds__(kScanWarps * 32)
 scores_warp_scan_f32(const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ covs,
