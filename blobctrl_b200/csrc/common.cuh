@@ -187,6 +187,16 @@ __device__ __forceinline__ float opacity_from_q2(float q2) {
   return fminf(__fdividef(2.0f, 1.0f + e), 1.0f);
 }
 
+// branch-free form for positive-definite blobs (the only kind the reference's callers produce)
+__device__ __forceinline__ float blob_opacity_pd(const BlobCoef& c, float xf, float yf) {
+  const float dy = (yf - c.cy_hi) - c.cy_lo;
+  const float dx = (xf - c.cx_hi) - c.cx_lo;
+  const float u = c.p * dx;
+  const float v = fmaf(c.r, dx, c.t * dy);
+  const float s = opacity_from_q2(fmaf(u, u, v * v));
+  return (c.flags & kGated) ? 1e-6f : s;
+}
+
 // raw opacity of one blob at one pixel (stage 1 + gate)
 __device__ __forceinline__ float blob_opacity(const BlobCoef& c, float xf, float yf) {
   if (c.flags & kGated) return 1e-6f;

@@ -48,9 +48,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint (ns)
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a CUDA error (trap) after ~2 s instead of a hung GPU.
@@ -58,6 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);   // keep the waiting warp out of the issue slots of the working warps on its SMSP
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
@@ -197,43 +198,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
       // =============================== stages 1+2 + operand staging ===============================
       const int tid = threadIdx.x;  // 0..127 == pixel within the tile == TMEM lane
       asm volatile("bar.sync 1, 128;" ::: "memory");   // previous unit's tiles are done with `coef`
+      uint32_t my_general = 0;
       for (int i = tid; i < p.M; i += 128) {
         const size_t b = (size_t)n * p.M + i;
         const float* c = p.covs + 4 * b;
-        coef[i] = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
-                                 (double)c[3], p.sizes[b], p.H, p.W);
+        const BlobCoef bc = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
+                                           (double)c[3], p.sizes[b], p.H, p.W);
+        my_general |= bc.flags & kGeneral;
+        coef[i] = bc;
       }
       if (unit_it > 0) mbar_wait(&bars->b_free, (unit_it - 1) & 1);   // MMAs of the previous unit have read B
       {
+        // features [K, C] (c contiguous) -> K-major 16-byte k-chunks per channel; 4 items (16 B each) per
+        // thread per round so 4*T global loads are in flight before the first conversion
         const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
         const int items = (p.Kp / kElemsPer16B) * p.c_tile;
-        for (int i = tid; i < items; i += 128) {
-          const int kc = i / p.c_tile, c = i - kc * p.c_tile;
-          const int ch = c0 + c;
-          float v[kElemsPer16B];
+        constexpr int kBatch = 4;
+        for (int i0 = tid; i0 < items; i0 += 128 * kBatch) {
+          float v[kBatch][kElemsPer16B];
 #pragma unroll
-          for (int j = 0; j < kElemsPer16B; ++j) {
-            const int k = kc * kElemsPer16B + j;
-            v[j] = (k < p.K && ch < p.C) ? (float)Cvt<FT>::to(f[(size_t)k * p.C + ch]) : 0.0f;
+          for (int b = 0; b < kBatch; ++b) {
+            const int i = i0 + b * 128;
+            const int kc = i / p.c_tile, c = i - kc * p.c_tile;
+            const int ch = c0 + c;
+#pragma unroll
+            for (int j = 0; j < kElemsPer16B; ++j) {
+              const int k = kc * kElemsPer16B + j;
+              v[b][j] = (i < items && k < p.K && ch < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch)) : 0.0f;
+            }
           }
-          unsigned char* dst = b_smem + (size_t)i * 16;
-          if constexpr (kTf32) {
-            float hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j]); lo[j] = rna_tf32(v[j] - hi[j]); }
-            *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(dst + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-          } else {
-            OT h[8];
+          for (int b = 0; b < kBatch; ++b) {
+            const int i = i0 + b * 128;
+            if (i >= items) break;
+            unsigned char* dst = b_smem + (size_t)i * 16;
+            if constexpr (kTf32) {
+              float hi[4], lo[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[j]);
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+              for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[b][j]); lo[j] = rna_tf32(v[b][j] - hi[j]); }
+              *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(dst + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
+              OT h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[b][j]);
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+            }
           }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
       mbar_arrive(&bars->b_full);
-      asm volatile("bar.sync 1, 128;" ::: "memory");                  // coef visible to all 128 threads
+      uint32_t any_general;   // barrier + OR-reduce: coef visible to all 128 threads; does any blob need the slow form?
+      asm volatile(
+          "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+          "barrier.cta.red.or.pred r, 1, 128, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+          : "=r"(any_general) : "r"(my_general) : "memory");
 
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
@@ -243,16 +263,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
         const float xf = (float)(live ? pix - y * p.W : 0), yf = (float)y;
         float T = 1.0f;
         float* my = stash + tid;
-#pragma unroll 4
-        for (int m = p.M - 1; m >= 0; --m) {
-          const float s = blob_opacity(coef[m], xf, yf);
+        const bool wr = comp != nullptr && live;
+        size_t off = (size_t)p.M * P + pix;            // plane k = M, walking down to the background plane
+        int m = p.M;
+        if (!any_general) {
+          // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
+          // transmittance T is a serial dependence (one FFMA per blob)
+          for (; m >= 8; m -= 8) {
+            float s[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d = s[j] * T;
+              T = fmaf(-s[j], T, T);
+              my[(size_t)(m - j) * kTcTileM] = d;
+              if (wr) __stcs(comp + off, Cvt<OT>::from(d));
+              off -= P;
+            }
+          }
+        }
+        for (; m >= 1; --m) {
+          const float s = blob_opacity(coef[m - 1], xf, yf);
           const float d = s * T;
           T = fmaf(-s, T, T);
-          my[(size_t)(m + 1) * kTcTileM] = d;
-          if (comp && live) __stcs(comp + (size_t)(m + 1) * P + pix, Cvt<OT>::from(d));
+          my[(size_t)m * kTcTileM] = d;
+          if (wr) __stcs(comp + off, Cvt<OT>::from(d));
+          off -= P;
         }
         my[0] = T;
-        if (comp && live) __stcs(comp + pix, Cvt<OT>::from(T));
+        if (wr) __stcs(comp + pix, Cvt<OT>::from(T));
         for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
 
         if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
@@ -306,20 +346,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
           mbar_wait(&bars->d_full[h], tile_it & 1);
           tc_fence_after();
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
-          for (int cc = 0; cc < c_half; cc += 32) {
-            uint32_t r[32];
-            if (c_half - cc >= 32) {
-              tmem_ld32(taddr + cc, r);
-            } else {                                 // c_half is a multiple of 16
-              tmem_ld16(taddr + cc, r);
-            }
+          OT* o = out + (size_t)(h * c_half) * P + pix;
+          const int ch_left = p.C - (c0 + h * c_half);          // valid channels in this half (may exceed c_half)
+          if (ch_left >= c_half && (c_half & 31) == 0) {
+            // fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
             tmem_wait_ld();
-            const int nvalid = min(32, c_half - cc);
-            OT* o = out + (size_t)(h * c_half + cc) * P + pix;
+            for (int cc = 0; cc < c_half; cc += 64) {
+              if (cc + 32 < c_half) tmem_ld32(taddr + cc + 32, rb);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nvalid && live && (c0 + h * c_half + cc + j) < p.C)
-                __stcs(o + (size_t)j * P, Cvt<OT>::from(__uint_as_float(r[j])));
+              for (int j = 0; j < 32; ++j) {
+                if (live) __stcs(o, Cvt<OT>::from(__uint_as_float(ra[j])));
+                o += P;
+              }
+              tmem_wait_ld();
+              if (cc + 32 < c_half) {
+                if (cc + 64 < c_half) tmem_ld32(taddr + cc + 64, ra);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  if (live) __stcs(o, Cvt<OT>::from(__uint_as_float(rb[j])));
+                  o += P;
+                }
+                tmem_wait_ld();
+              }
+            }
+          } else {
+            for (int cc = 0; cc < c_half; cc += 16) {           // c_half is a multiple of 16
+              uint32_t r[16];
+              tmem_ld16(taddr + cc, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (live && cc + j < ch_left) __stcs(o, Cvt<OT>::from(__uint_as_float(r[j])));
+                o += P;
+              }
             }
           }
           tc_fence_before();
