@@ -19,17 +19,22 @@
 // bar, at 1/3 of TF32 rate which still leaves the tensor pipe at ~50% of the HBM-bound tile time.
 // bf16/f16 maps use one kind::f16 MMA per k-step.
 //
-// Warp roles (288 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
-//   warps 0-3  stages 1+2 for one 128-pixel tile: d_k -> global composed planes (coalesced) and a
-//              shared-memory stash; then, once the MMA has released A, stash -> hi/lo -> tcgen05.st.
-//              Also stage the unit's features (B) and blob coefficients.
-//   warps 4-7  epilogue: tcgen05.ld D half -> registers -> coalesced global stores of [N,C,H,W].
-//   warp  8    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit to mbarriers.
+// Warp roles (416 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
+//   warps 0-7   stages 1+2 for one 128-pixel tile, two warps per TMEM lane quarter: each composites one
+//               of two blob ranges (a two-level multiplicative suffix scan across blobs, carry through
+//               shared memory), d_k -> global composed planes (coalesced) and a shared-memory stash;
+//               then, once the MMA has released A, stash -> hi/lo -> tcgen05.st.  Also stage the unit's
+//               features (B) and blob coefficients.
+//   warps 8-11  epilogue: tcgen05.ld D half -> registers -> coalesced global stores of [N,C,H,W].
+//   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit to mbarriers.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace blobsplat {
 
-constexpr int kTcThreads = 288;
+// kHalves = 1: 4 compute warps (one per TMEM lane quarter); kHalves = 2: 8 compute warps, two per quarter, each
+// compositing one of two blob ranges.  Threads = (4*kHalves compute + 4 epilogue + 1 MMA) warps = 288 / 416.
 constexpr int kTcTileM = 128;
 constexpr int kTcMaxCTile = 320;
 constexpr int kTcMaxBlobs = 127;                 // coefficient table: 127 * 32 B
@@ -143,8 +148,11 @@ struct TcBarriers {
 };
 
 // FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
-template <typename FT, typename OT, bool kTf32>
-__global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTcParams p) {
+template <typename FT, typename OT, bool kTf32, int kHalves>
+__global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const RenderTcParams p) {
+  constexpr int kTcComputeWarps = 4 * kHalves;
+  constexpr int kTcComputeThreads = kTcComputeWarps * 32;
+  constexpr int kTcMmaWarp = kTcComputeWarps + 4;
   extern __shared__ __align__(1024) unsigned char smem[];
   using BT = typename std::conditional<kTf32, float, OT>::type;   // element type of B in smem (tf32 bits or bf16/f16)
   constexpr int kElemsPer16B = 16 / sizeof(BT);                    // T: 4 (tf32) or 8 (16-bit)
@@ -157,15 +165,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
   const size_t b_bytes = (size_t)(p.Kp / kElemsPer16B) * p.c_tile * 16;   // one B copy
   unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
   float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [Kp][128] composed weights of one tile
-  BlobCoef* coef = reinterpret_cast<BlobCoef*>(stash + (size_t)p.Kp * kTcTileM);
+  float* carry = stash + (size_t)p.Kp * kTcTileM;                         // [128] front-range transmittance per pixel
+  BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     if (lane == 0) {
-      mbar_init(&bars->a_full, 128); mbar_init(&bars->a_free, 1);
-      mbar_init(&bars->b_full, 128); mbar_init(&bars->b_free, 1);
+      mbar_init(&bars->a_full, kTcComputeThreads); mbar_init(&bars->a_free, 1);
+      mbar_init(&bars->b_full, kTcComputeThreads); mbar_init(&bars->b_free, 1);
       mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
       mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -194,12 +203,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
     const int t_hi = min(t_lo + p.tiles_per_unit, p.tiles_per_image);
     const int ntiles = t_hi - t_lo;
 
-    if (warp < 4) {
+    if (warp < kTcComputeWarps) {
       // =============================== stages 1+2 + operand staging ===============================
-      const int tid = threadIdx.x;  // 0..127 == pixel within the tile == TMEM lane
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // previous unit's tiles are done with `coef`
+      // 8 warps: two per TMEM lane quarter.  Warp (half, q) owns pixels q*32..q*32+31 of the tile and one of
+      // two contiguous blob ranges: half 0 the front (high-index) range, half 1 the back range + background.
+      const int ctid = threadIdx.x;                 // 0..255
+      const int half = warp >> 2, q = warp & 3;
+      const int px = q * 32 + lane;                 // pixel within the tile == TMEM lane
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
       uint32_t my_general = 0;
-      for (int i = tid; i < p.M; i += 128) {
+      for (int i = ctid; i < p.M; i += kTcComputeThreads) {
         const size_t b = (size_t)n * p.M + i;
         const float* c = p.covs + 4 * b;
         const BlobCoef bc = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
@@ -214,11 +227,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
         const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
         const int items = (p.Kp / kElemsPer16B) * p.c_tile;
         constexpr int kBatch = 4;
-        for (int i0 = tid; i0 < items; i0 += 128 * kBatch) {
+        for (int i0 = ctid; i0 < items; i0 += kTcComputeThreads * kBatch) {
           float v[kBatch][kElemsPer16B];
 #pragma unroll
           for (int b = 0; b < kBatch; ++b) {
-            const int i = i0 + b * 128;
+            const int i = i0 + b * kTcComputeThreads;
             const int kc = i / p.c_tile, c = i - kc * p.c_tile;
             const int ch = c0 + c;
 #pragma unroll
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
           }
 #pragma unroll
           for (int b = 0; b < kBatch; ++b) {
-            const int i = i0 + b * 128;
+            const int i = i0 + b * kTcComputeThreads;
             if (i >= items) break;
             unsigned char* dst = b_smem + (size_t)i * 16;
             if constexpr (kTf32) {
@@ -249,27 +262,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
       mbar_arrive(&bars->b_full);
-      uint32_t any_general;   // barrier + OR-reduce: coef visible to all 128 threads; does any blob need the slow form?
+      uint32_t any_general;   // barrier + OR-reduce: coef visible to all compute threads; does any blob need the slow form?
       asm volatile(
           "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
-          "barrier.cta.red.or.pred r, 1, 128, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
-          : "=r"(any_general) : "r"(my_general) : "memory");
+          "barrier.cta.red.or.pred r, 1, %2, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+          : "=r"(any_general) : "r"(my_general), "n"(kTcComputeThreads) : "memory");
 
+      // Two-level multiplicative suffix scan across blobs: each range is composited with a local
+      // transmittance; the back range is then scaled by the front range's total transmittance.
+      // The back range carries the extra rescale pass, so it gets the smaller share (7/16) of the blobs.
+      const int m_split = kHalves == 2 ? (p.M * 7) >> 4 : 0;
+      const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
+      const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
-        const int pix = (t_lo + t) * kTcTileM + tid;
+        const int pix = (t_lo + t) * kTcTileM + px;
         const bool live = pix < P;
         const int y = live ? pix / p.W : 0;
         const float xf = (float)(live ? pix - y * p.W : 0), yf = (float)y;
         float T = 1.0f;
-        float* my = stash + tid;
+        float* my = stash + px;
         const bool wr = comp != nullptr && live;
-        size_t off = (size_t)p.M * P + pix;            // plane k = M, walking down to the background plane
-        int m = p.M;
+        const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
+        size_t off = (size_t)m_hi * P + pix;          // plane k = m_hi, walking down
+        int m = m_hi;
         if (!any_general) {
           // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
           // transmittance T is a serial dependence (one FFMA per blob)
-          for (; m >= 8; m -= 8) {
+          for (; m >= m_lo + 8; m -= 8) {
             float s[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
@@ -278,65 +298,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
               const float d = s[j] * T;
               T = fmaf(-s[j], T, T);
               my[(size_t)(m - j) * kTcTileM] = d;
-              if (wr) __stcs(comp + off, Cvt<OT>::from(d));
+              if (wr_now) __stcs(comp + off, Cvt<OT>::from(d));
               off -= P;
             }
           }
         }
-        for (; m >= 1; --m) {
+        for (; m >= m_lo + 1; --m) {
           const float s = blob_opacity(coef[m - 1], xf, yf);
           const float d = s * T;
           T = fmaf(-s, T, T);
           my[(size_t)m * kTcTileM] = d;
-          if (wr) __stcs(comp + off, Cvt<OT>::from(d));
+          if (wr_now) __stcs(comp + off, Cvt<OT>::from(d));
           off -= P;
         }
-        my[0] = T;
-        if (wr) __stcs(comp + pix, Cvt<OT>::from(T));
-        for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
+        if constexpr (kHalves == 2) {
+          if (half == 0) carry[px] = T;
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        }
+        if (half == kHalves - 1) {
+          float c = 1.0f;
+          if constexpr (kHalves == 2) {
+            c = carry[px];
+            off = (size_t)m_hi * P + pix;
+            for (int k = m_hi; k >= 1; --k) {
+              const float v = my[(size_t)k * kTcTileM] * c;
+              my[(size_t)k * kTcTileM] = v;
+              if (wr) __stcs(comp + off, Cvt<OT>::from(v));
+              off -= P;
+            }
+          }
+          const float bg = T * c;                     // background: alpha 1 * total transmittance
+          my[0] = bg;
+          if (wr) __stcs(comp + pix, Cvt<OT>::from(bg));
+        }
+        if (half == 0) {
+          for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
+        }
+        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
 
         if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
         tc_fence_after();
-        const uint32_t lane_addr = ((uint32_t)(warp * 32) << 16);
-        for (int g = 0; g < p.Kp / 8; ++g) {
-          float w[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) w[j] = live ? my[(size_t)(g * 8 + j) * kTcTileM] : 0.0f;
-          if constexpr (kTf32) {
+        const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+        if constexpr (kTf32) {
+          for (int g = half; g < p.Kp / 8; g += kHalves) {  // the warps of a quarter interleave the k-groups
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float h = rna_tf32(w[j]);
+              const float w = live ? my[(size_t)(g * 8 + j) * kTcTileM] : 0.0f;
+              const float h = rna_tf32(w);
               hi[j] = __float_as_uint(h);
-              lo[j] = __float_as_uint(rna_tf32(w[j] - h));
+              lo[j] = __float_as_uint(rna_tf32(w - h));
             }
             tmem_st8(tmem_a + lane_addr + g * 8, hi);
             tmem_st8(tmem_a + lane_addr + a_cols + g * 8, lo);
-          } else {
-            // two k per 32-bit column (low half = even k); 8 columns = 16 k, so pair groups g, g+1
-            if ((g & 1) == 0) {
-              float w2[8];
+          }
+        } else {
+          // two k per 32-bit column (low half = even k): 8 columns = 16 consecutive k
+          for (int g = half; g < p.Kp / 16; g += kHalves) {
+            uint32_t pk[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) w2[j] = live ? my[(size_t)((g + 1) * 8 + j) * kTcTileM] : 0.0f;
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                OT lo16 = Cvt<OT>::from(w[2 * j]), hi16 = Cvt<OT>::from(w[2 * j + 1]);
-                pk[j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo16)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi16)) << 16);
-                OT lo2 = Cvt<OT>::from(w2[2 * j]), hi2 = Cvt<OT>::from(w2[2 * j + 1]);
-                pk[4 + j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo2)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi2)) << 16);
-              }
-              tmem_st8(tmem_a + lane_addr + (g >> 1) * 8, pk);
+            for (int j = 0; j < 8; ++j) {
+              const float w0 = live ? my[(size_t)(g * 16 + 2 * j) * kTcTileM] : 0.0f;
+              const float w1 = live ? my[(size_t)(g * 16 + 2 * j + 1) * kTcTileM] : 0.0f;
+              OT lo16 = Cvt<OT>::from(w0), hi16 = Cvt<OT>::from(w1);
+              pk[j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo16)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi16)) << 16);
             }
+            tmem_st8(tmem_a + lane_addr + g * 8, pk);
           }
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->a_full);
+        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
       }
-    } else if (warp < 8) {
+    } else if (warp < kTcComputeWarps + 4) {
       // ========================================= epilogue ==========================================
-      const int q = warp - 4;                      // TMEM lane quarter
+      const int q = warp - kTcComputeWarps;        // TMEM lane quarter
       OT* out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
         const int pix = (t_lo + t) * kTcTileM + q * 32 + lane;
@@ -426,13 +463,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) render_tc_kernel(const RenderTc
   }
 
   // the last commits arrive asynchronously: see them land before the CTA (and its smem barriers) goes away
-  if (warp == 8 && lane == 0 && tile_it > 0) {
+  if (warp == kTcMmaWarp && lane == 0 && tile_it > 0) {
     mbar_wait(&bars->a_free, (tile_it - 1) & 1);
     mbar_wait(&bars->b_free, (unit_it - 1) & 1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
@@ -451,7 +488,7 @@ static TcPlan plan_tc(int K, int C, bool tf32) {
   if (C % 32 != 0) { pl.why = "C must be a multiple of 32 for the tensor-core render"; return pl; }
   const int a_cols = tf32 ? 2 * pl.Kp : pl.Kp / 2;
   const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : 2);                  // B bytes per channel (hi+lo fp32 | 16-bit)
-  const size_t fixed = (size_t)pl.Kp * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 1024;
+  const size_t fixed = (size_t)pl.Kp * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
   int c_tile = std::min(kTcMaxCTile, C);
   c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
@@ -477,13 +514,13 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
   return 1;
 }
 
-template <typename FT, typename OT, bool kTf32>
+template <typename FT, typename OT, bool kTf32, int kHalves>
 static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
   static thread_local int sm_count = 0, sm_dev = -1;
@@ -492,7 +529,7 @@ static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
     sm_dev = dev;
   }
   const int grid = std::min(sm_count, p.total_units);
-  render_tc_kernel<FT, OT, kTf32><<<grid, kTcThreads, smem, st>>>(p);
+  render_tc_kernel<FT, OT, kTf32, kHalves><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(p);
   BS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -523,9 +560,18 @@ int render_tc_dispatch(const float* xs, const float* ys, const float* covs, cons
   const long long total = base_units * p.segs;
   if (total > 0x7fffffffll) BS_UNSUPPORTED("too many work units");
   p.total_units = (int)total;
-  if (tf32) return launch_tc<float, float, true>(p, pl.smem, st);
-  if (out_dtype == BLOBSPLAT_BF16) return launch_tc<__nv_bfloat16, __nv_bfloat16, false>(p, pl.smem, st);
-  if (out_dtype == BLOBSPLAT_F16) return launch_tc<__half, __half, false>(p, pl.smem, st);
+  // 8 compute warps (kHalves = 2) win for every dtype once the GPU settles at its sustained clocks
+  // (A/B in profiles/ab_compute_warps_r1.txt: fp32 1.45 vs 1.55 ms, bf16 1.09 vs 1.17 ms); the 4-warp form is
+  // only ahead for the first few launches on a cold, full-clock GPU.
+  // BLOBSPLAT_TC_HALVES=1|2 overrides the choice (tuning knob for A/B measurements; read per call, no state).
+  int halves = 2;
+  if (const char* e = getenv("BLOBSPLAT_TC_HALVES")) { if (e[0] == '1') halves = 1; else if (e[0] == '2') halves = 2; }
+  if (tf32) return halves == 1 ? launch_tc<float, float, true, 1>(p, pl.smem, st) : launch_tc<float, float, true, 2>(p, pl.smem, st);
+  if (out_dtype == BLOBSPLAT_BF16)
+    return halves == 1 ? launch_tc<__nv_bfloat16, __nv_bfloat16, false, 1>(p, pl.smem, st)
+                       : launch_tc<__nv_bfloat16, __nv_bfloat16, false, 2>(p, pl.smem, st);
+  if (out_dtype == BLOBSPLAT_F16)
+    return halves == 1 ? launch_tc<__half, __half, false, 1>(p, pl.smem, st) : launch_tc<__half, __half, false, 2>(p, pl.smem, st);
   BS_UNSUPPORTED("fused render: unsupported dtype %d", out_dtype);
 }
 
