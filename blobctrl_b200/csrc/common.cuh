@@ -187,13 +187,29 @@ __device__ __forceinline__ float opacity_from_q2(float q2) {
   return fminf(__fdividef(2.0f, 1.0f + e), 1.0f);
 }
 
+// same with the "-1" already folded into the exponent: s = 1 / (0.5 + 2^(q' - 1)) — one MUFU.EX2, one FADD,
+// one MUFU.RCP (no multiply by 2)
+__device__ __forceinline__ float opacity_from_q2m1(float q2m1) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q2m1));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(0.5f + e));
+  return fminf(r, 1.0f);
+}
+
 // branch-free form for positive-definite blobs (the only kind the reference's callers produce)
 __device__ __forceinline__ float blob_opacity_pd(const BlobCoef& c, float xf, float yf) {
   const float dy = (yf - c.cy_hi) - c.cy_lo;
   const float dx = (xf - c.cx_hi) - c.cx_lo;
   const float u = c.p * dx;
   const float v = fmaf(c.r, dx, c.t * dy);
+#ifndef BS_FOLD
+#define BS_FOLD 1
+#endif
+#if BS_FOLD
+  const float s = opacity_from_q2m1(fmaf(u, u, fmaf(v, v, -1.0f)));
+#else
   const float s = opacity_from_q2(fmaf(u, u, v * v));
+#endif
   return (c.flags & kGated) ? 1e-6f : s;
 }
 

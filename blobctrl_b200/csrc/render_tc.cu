@@ -31,6 +31,11 @@
 
 #include "common.cuh"
 
+// compile-time tuning knobs (scripts/ab_variants.py builds variants and A/Bs them in one process)
+#ifndef BS_RNA_CUSTOM
+#define BS_RNA_CUSTOM 1
+#endif
+
 namespace blobsplat {
 
 // kHalves = 1: 4 compute warps (one per TMEM lane quarter); kHalves = 2: 8 compute warps, two per quarter, each
@@ -58,14 +63,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint (ns)
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a CUDA error (trap) after ~2 s instead of a hung GPU.
+// Bounded wait: a protocol bug becomes a CUDA error (trap) after ~2 s instead of a hung GPU.  try_wait already
+// suspends the warp in hardware for a while; the optional nanosleep trades wake-up latency for issue slots.
+#ifndef BS_SPIN_SLEEP_NS
+#define BS_SPIN_SLEEP_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  uint32_t spins = 0;
+#ifdef BS_PREV_WAIT
+  (void)spins;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);   // keep the waiting warp out of the issue slots of the working warps on its SMSP
+    __nanosleep(40);
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+    if (BS_SPIN_SLEEP_NS > 0) __nanosleep(BS_SPIN_SLEEP_NS);
+    if (((++spins) & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+#endif
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -126,10 +144,16 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t n) {
   return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
 }
 
+// Round-to-nearest (ties away) to TF32's 10 explicit mantissa bits: (bits + 0x1000) & ~0x1fff.  Same result as
+// cvt.rna.tf32.f32 for finite values (weights are in [0,1], features finite) at 2 integer ops instead of ~5.
 __device__ __forceinline__ float rna_tf32(float x) {
+#if BS_RNA_CUSTOM
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#else
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+#endif
 }
 
 struct RenderTcParams {
@@ -148,7 +172,9 @@ struct TcBarriers {
 };
 
 // FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
-template <typename FT, typename OT, bool kTf32, int kHalves>
+// kP: pixels per image when it is one of the common sizes (64^2, 32^2, 16^2), else 0 = runtime.  With a
+// compile-time plane stride every store of an unrolled group is [base + immediate]: no address arithmetic.
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP>
 __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const RenderTcParams p) {
   constexpr int kTcComputeWarps = 4 * kHalves;
   constexpr int kTcComputeThreads = kTcComputeWarps * 32;
@@ -160,7 +186,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   constexpr int kNumB = kTf32 ? 2 : 1;                             // hi + lo
   constexpr int kACols = kTf32 ? 1 : 2;                            // k elements per 32-bit TMEM column
 
-  const int P = p.H * p.W;
+  const int P = kP > 0 ? kP : p.H * p.W;
   const int c_half = p.c_tile >> 1;
   const size_t b_bytes = (size_t)(p.Kp / kElemsPer16B) * p.c_tile * 16;   // one B copy
   unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
@@ -271,7 +297,10 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       // Two-level multiplicative suffix scan across blobs: each range is composited with a local
       // transmittance; the back range is then scaled by the front range's total transmittance.
       // The back range carries the extra rescale pass, so it gets the smaller share (7/16) of the blobs.
-      const int m_split = kHalves == 2 ? (p.M * 7) >> 4 : 0;
+#ifndef BS_SPLIT_NUM
+#define BS_SPLIT_NUM 7
+#endif
+      const int m_split = kHalves == 2 ? (((p.M * BS_SPLIT_NUM) >> 4) & ~3) : 0;   // multiple of 4: whole unrolled groups
       const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
       const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
@@ -284,7 +313,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
         float* my = stash + px;
         const bool wr = comp != nullptr && live;
         const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
-        size_t off = (size_t)m_hi * P + pix;          // plane k = m_hi, walking down
+        OT* const comp_px = comp + pix;                 // this pixel in plane 0; plane k is + k*P
         int m = m_hi;
         if (!any_general) {
           // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
@@ -294,22 +323,21 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
 #pragma unroll
             for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
 #pragma unroll
+            OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
             for (int j = 0; j < 8; ++j) {
               const float d = s[j] * T;
               T = fmaf(-s[j], T, T);
               my[(size_t)(m - j) * kTcTileM] = d;
-              if (wr_now) __stcs(comp + off, Cvt<OT>::from(d));
-              off -= P;
+              if (wr_now) __stcs(cp - (ptrdiff_t)j * P, Cvt<OT>::from(d));
             }
           }
         }
         for (; m >= m_lo + 1; --m) {
-          const float s = blob_opacity(coef[m - 1], xf, yf);
+          const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
           const float d = s * T;
           T = fmaf(-s, T, T);
           my[(size_t)m * kTcTileM] = d;
-          if (wr_now) __stcs(comp + off, Cvt<OT>::from(d));
-          off -= P;
+          if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
         }
         if constexpr (kHalves == 2) {
           if (half == 0) carry[px] = T;
@@ -319,17 +347,16 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           float c = 1.0f;
           if constexpr (kHalves == 2) {
             c = carry[px];
-            off = (size_t)m_hi * P + pix;
+#pragma unroll 4
             for (int k = m_hi; k >= 1; --k) {
               const float v = my[(size_t)k * kTcTileM] * c;
               my[(size_t)k * kTcTileM] = v;
-              if (wr) __stcs(comp + off, Cvt<OT>::from(v));
-              off -= P;
+              if (wr) __stcs(comp_px + (size_t)k * P, Cvt<OT>::from(v));
             }
           }
           const float bg = T * c;                     // background: alpha 1 * total transmittance
           my[0] = bg;
-          if (wr) __stcs(comp + pix, Cvt<OT>::from(bg));
+          if (wr) __stcs(comp_px, Cvt<OT>::from(bg));
         }
         if (half == 0) {
           for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
@@ -383,7 +410,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           mbar_wait(&bars->d_full[h], tile_it & 1);
           tc_fence_after();
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
-          OT* o = out + (size_t)(h * c_half) * P + pix;
+          OT* const o = out + (size_t)(h * c_half) * P + pix;   // this pixel in the half's first channel plane
           const int ch_left = p.C - (c0 + h * c_half);          // valid channels in this half (may exceed c_half)
           if (ch_left >= c_half && (c_half & 31) == 0) {
             // fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
@@ -392,19 +419,17 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             tmem_wait_ld();
             for (int cc = 0; cc < c_half; cc += 64) {
               if (cc + 32 < c_half) tmem_ld32(taddr + cc + 32, rb);
+              OT* oc = o + (size_t)cc * P;                       // chunk base; the 32 planes are immediates when kP > 0
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (live) __stcs(o, Cvt<OT>::from(__uint_as_float(ra[j])));
-                o += P;
-              }
+              for (int j = 0; j < 32; ++j)
+                if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(ra[j])));
               tmem_wait_ld();
               if (cc + 32 < c_half) {
                 if (cc + 64 < c_half) tmem_ld32(taddr + cc + 64, ra);
+                oc += (size_t)32 * P;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  if (live) __stcs(o, Cvt<OT>::from(__uint_as_float(rb[j])));
-                  o += P;
-                }
+                for (int j = 0; j < 32; ++j)
+                  if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(rb[j])));
                 tmem_wait_ld();
               }
             }
@@ -414,10 +439,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
               tmem_ld16(taddr + cc, r);
               tmem_wait_ld();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (live && cc + j < ch_left) __stcs(o, Cvt<OT>::from(__uint_as_float(r[j])));
-                o += P;
-              }
+              for (int j = 0; j < 16; ++j)
+                if (live && cc + j < ch_left) __stcs(o + (size_t)(cc + j) * P, Cvt<OT>::from(__uint_as_float(r[j])));
             }
           }
           tc_fence_before();
@@ -514,13 +537,13 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
   return 1;
 }
 
-template <typename FT, typename OT, bool kTf32, int kHalves>
-static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP>
+static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves, kP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
   static thread_local int sm_count = 0, sm_dev = -1;
@@ -529,9 +552,21 @@ static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
     sm_dev = dev;
   }
   const int grid = std::min(sm_count, p.total_units);
-  render_tc_kernel<FT, OT, kTf32, kHalves><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(p);
+  render_tc_kernel<FT, OT, kTf32, kHalves, kP><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(p);
   BS_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <typename FT, typename OT, bool kTf32, int kHalves>
+static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
+  if constexpr (kHalves == 2) {   // plane-stride specialisations for BlobNet's latent resolutions (64/32/16)
+    switch (p.H * p.W) {
+      case 4096: return launch_tc_p<FT, OT, kTf32, kHalves, 4096>(p, smem, st);
+      case 1024: return launch_tc_p<FT, OT, kTf32, kHalves, 1024>(p, smem, st);
+      case 256: return launch_tc_p<FT, OT, kTf32, kHalves, 256>(p, smem, st);
+    }
+  }
+  return launch_tc_p<FT, OT, kTf32, kHalves, 0>(p, smem, st);
 }
 
 int render_tc_dispatch(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,

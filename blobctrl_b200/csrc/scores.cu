@@ -79,7 +79,7 @@ scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys
           for (int j = 0; j < V; ++j) {
             const float u = fmaf((float)j, c.p, u0);
             const float v = fmaf((float)j, c.r, v0);
-            s[j] = opacity_from_q2(fmaf(u, u, v * v));
+            s[j] = opacity_from_q2m1(fmaf(u, u, fmaf(v, v, -1.0f)));
           }
         } else {
 #pragma unroll
