@@ -28,6 +28,8 @@ int resize_dispatch(const void*, void*, int, int, int, int, int, int, cudaStream
 int pyramid_dispatch(const void*, void* const*, int, int, int, int, cudaStream_t);
 int feature_splat_fma_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int,
                                int, cudaStream_t);
+int feature_splat_tc_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int, int,
+                              cudaStream_t);
 int render_tc_dispatch(const float*, const float*, const float*, const float*, const void*, int, int, int, int, int,
                        int, void*, void*, int, cudaStream_t);
 int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why);
@@ -131,11 +133,16 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
   BS_CHECK_ARG(stride_k >= 0 && stride_p >= 1 && stride_n >= 0, "bad strides");
   if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(scores && features && out, "NULL pointer");
-  if (engine == BLOBSPLAT_ENGINE_TENSOR)
-    BS_UNSUPPORTED("stand-alone stage 3 runs on the FMA engine; the tensor-core engine is the fused "
-                   "blobsplat_render (weights are produced on-chip as the TMEM operand)");
   DeviceGuard g(device);
   if (g.status) return g.status;
+  // Stage 3 is a dense contraction [P x K] x [K x C]: on tensor cores (tcgen05, weights staged into TMEM) when
+  // K and C make it one, on CUDA-core FMA tiles otherwise (tiny K: the K = 1 pipeline splat, C = 3 previews).
+  const char* why = nullptr;
+  const bool tc_ok = dtype != BLOBSPLAT_F64 && render_tc_supported(K, C, H, W, dtype, dtype, &why);
+  if (engine == BLOBSPLAT_ENGINE_TENSOR && !tc_ok) BS_UNSUPPORTED("tensor-core feature splat: %s", why ? why : "float64");
+  if (tc_ok && (engine == BLOBSPLAT_ENGINE_TENSOR || (engine == BLOBSPLAT_ENGINE_AUTO && K >= 12 && C >= 64)))
+    return feature_splat_tc_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
+                                     (cudaStream_t)stream);
   return feature_splat_fma_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
                                     (cudaStream_t)stream);
 }

@@ -1,0 +1,632 @@
+// Fused render — stages 1+2+3 in ONE persistent, warp-specialised kernel on tcgen05 tensor cores.
+//
+// Replaces the whole of splat_features (blobctrl/utils/utils.py:80-241) for interp_size ==
+// score_size: blob parameters + features [N,K,C] -> composed maps [N,K,H,W] and feature grid
+// [N,C,H,W].  The per-pixel weights never leave the SM:
+//
+//   D[pixel, channel] = sum_k A[pixel, k] * B[k, channel]         (M = 128 pixels, N = C tile, K = M_blobs+1)
+//
+//   A  the composed weights d_k, produced by stages 1+2 on CUDA cores (lane = pixel, the serial
+//      front-to-back walk of scores.cu) and written with tcgen05.st straight into TENSOR MEMORY —
+//      TMEM lane = pixel, column = k — i.e. the MMA's A operand lives in TMEM (".ts" form).
+//   B  the image's features, staged once per work unit in shared memory in the canonical K-major
+//      no-swizzle UMMA layout (8-row x 16-byte core matrices; SBO = 128 B, LBO = C_tile*16 B).
+//   D  fp32 accumulators in TMEM (C_tile <= 320 columns), split in two channel halves so the MMA of
+//      half h of tile t+1 overlaps the drain of the other half of tile t.
+//
+// Precision: float32 maps use the 3xTF32 split (hi = rna_tf32(x), lo = rna_tf32(x - hi);
+// D = Ahi*Bhi + Ahi*Blo + Alo*Bhi, fp32 accumulate) — product error ~3*2^-22, inside the 1e-5 parity
+// bar, at 1/3 of TF32 rate which still leaves the tensor pipe at ~50% of the HBM-bound tile time.
+// bf16/f16 maps use one kind::f16 MMA per k-step.
+//
+// Warp roles (416 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
+//   warps 0-7   stages 1+2 for one 128-pixel tile, two warps per TMEM lane quarter: each composites one
+//               of two blob ranges (a two-level multiplicative suffix scan across blobs, carry through
+//               shared memory), d_k -> global composed planes (coalesced) and a shared-memory stash;
+//               then, once the MMA has released A, stash -> hi/lo -> tcgen05.st.  Also stage the unit's
+//               features (B) and blob coefficients.
+//   warps 8-11  epilogue: tcgen05.ld D half -> registers -> coalesced global stores of [N,C,H,W].
+//   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit to mbarriers.
+#pragma once
+#include <cstdlib>
+
+#include "common.cuh"
+
+// compile-time tuning knobs (scripts/ab_variants.py builds variants and A/Bs them in one process)
+#ifndef BS_RNA_CUSTOM
+#define BS_RNA_CUSTOM 1
+#endif
+
+namespace blobsplat {
+
+// kHalves = 1: 4 compute warps (one per TMEM lane quarter); kHalves = 2: 8 compute warps, two per quarter, each
+// compositing one of two blob ranges.  Threads = (4*kHalves compute + 4 epilogue + 1 MMA) warps = 288 / 416.
+constexpr int kTcTileM = 128;
+constexpr int kTcMaxCTile = 320;
+constexpr int kTcMaxBlobs = 127;                 // coefficient table: 127 * 32 B
+constexpr size_t kTcSmemBudget = 227 * 1024 - 256;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");   // suspend-time hint (ns)
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a CUDA error (trap) after ~2 s instead of a hung GPU.  try_wait already
+// suspends the warp in hardware for a while; the optional nanosleep trades wake-up latency for issue slots.
+#ifndef BS_SPIN_SLEEP_NS
+#define BS_SPIN_SLEEP_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+#ifdef BS_PREV_WAIT
+  (void)spins;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+#else
+  while (!mbar_try_wait(bar, parity)) {
+    if (BS_SPIN_SLEEP_NS > 0) __nanosleep(BS_SPIN_SLEEP_NS);
+    if (((++spins) & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
+  }
+#endif
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+template <bool kTf32>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1 | [61,64) layout = 0
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10, K-major both, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t n) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
+}
+
+// Round-to-nearest (ties away) to TF32's 10 explicit mantissa bits: (bits + 0x1000) & ~0x1fff.  Same result as
+// cvt.rna.tf32.f32 for finite values (weights are in [0,1], features finite) at 2 integer ops instead of ~5.
+__device__ __forceinline__ float rna_tf32(float x) {
+#if BS_RNA_CUSTOM
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+#else
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+#endif
+}
+
+struct RenderTcParams {
+  const float* xs; const float* ys; const float* covs; const float* sizes;
+  const void* scores; long long sn, sk, sp;   // kFromScores: precomputed weights [N,K,P] with element strides
+  const void* feats; void* composed; void* grid;
+  int N, M, H, W, C;
+  int K, Kp;              // K = M + 1; Kp = K rounded up to the MMA k-step (8 tf32 / 16 f16)
+  int c_tile, c_chunks;   // channels per work unit (multiple of 32, <= 320); ceil(C / c_tile)
+  int tiles_per_image, tiles_per_unit, segs;  // 128-pixel tiles; unit = (image, chunk, tile segment)
+  int total_units;
+};
+
+struct TcBarriers {
+  uint64_t a_full, a_free, b_full, b_free, d_full[2], d_empty[2];
+  uint32_t tmem_base;
+};
+
+// FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
+// kP: pixels per image when it is one of the common sizes (64^2, 32^2, 16^2), else 0 = runtime.  With a
+// compile-time plane stride every store of an unrolled group is [base + immediate]: no address arithmetic.
+// kFromScores: the A operand comes from precomputed score maps in global memory (stand-alone stage 3,
+// splat_features_from_scores) instead of being rendered from blob parameters (stages 1+2).
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
+__global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const RenderTcParams p) {
+  constexpr int kTcComputeWarps = 4 * kHalves;
+  constexpr int kTcComputeThreads = kTcComputeWarps * 32;
+  constexpr int kTcMmaWarp = kTcComputeWarps + 4;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  using BT = typename std::conditional<kTf32, float, OT>::type;   // element type of B in smem (tf32 bits or bf16/f16)
+  constexpr int kElemsPer16B = 16 / sizeof(BT);                    // T: 4 (tf32) or 8 (16-bit)
+  constexpr int kKStep = 2 * kElemsPer16B;                         // K per MMA: 8 or 16
+  constexpr int kNumB = kTf32 ? 2 : 1;                             // hi + lo
+  constexpr int kACols = kTf32 ? 1 : 2;                            // k elements per 32-bit TMEM column
+
+  const int P = kP > 0 ? kP : p.H * p.W;
+  const int c_half = p.c_tile >> 1;
+  const size_t b_bytes = (size_t)(p.Kp / kElemsPer16B) * p.c_tile * 16;   // one B copy
+  unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
+  float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [Kp][128] composed weights of one tile
+  float* carry = stash + (size_t)p.Kp * kTcTileM;                         // [128] front-range transmittance per pixel
+  BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == kTcMmaWarp) {
+    if (lane == 0) {
+      mbar_init(&bars->a_full, kTcComputeThreads); mbar_init(&bars->a_free, 1);
+      mbar_init(&bars->b_full, kTcComputeThreads); mbar_init(&bars->b_free, 1);
+      mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
+      mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem_a = tmem + (uint32_t)p.c_tile;              // A hi; A lo follows at + Kp/kACols columns
+  const int a_cols = p.Kp / kACols;
+
+  int unit_it = 0;      // units processed by this CTA so far
+  int tile_it = 0;      // tiles processed by this CTA so far (barrier phases)
+
+  for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++unit_it) {
+    const int per_image = p.c_chunks * p.segs;
+    const int n = unit / per_image;
+    const int rem = unit - n * per_image;
+    const int chunk = rem / p.segs, seg = rem - chunk * p.segs;
+    const int c0 = chunk * p.c_tile;
+    const int t_lo = seg * p.tiles_per_unit;
+    const int t_hi = min(t_lo + p.tiles_per_unit, p.tiles_per_image);
+    const int ntiles = t_hi - t_lo;
+
+    if (warp < kTcComputeWarps) {
+      // =============================== stages 1+2 + operand staging ===============================
+      // 8 warps: two per TMEM lane quarter.  Warp (half, q) owns pixels q*32..q*32+31 of the tile and one of
+      // two contiguous blob ranges: half 0 the front (high-index) range, half 1 the back range + background.
+      const int ctid = threadIdx.x;                 // 0..255
+      const int half = warp >> 2, q = warp & 3;
+      const int px = q * 32 + lane;                 // pixel within the tile == TMEM lane
+      asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
+      uint32_t my_general = 0;
+      if constexpr (!kFromScores)
+      for (int i = ctid; i < p.M; i += kTcComputeThreads) {
+        const size_t b = (size_t)n * p.M + i;
+        const float* c = p.covs + 4 * b;
+        const BlobCoef bc = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
+                                           (double)c[3], p.sizes[b], p.H, p.W);
+        my_general |= bc.flags & kGeneral;
+        coef[i] = bc;
+      }
+      if (unit_it > 0) mbar_wait(&bars->b_free, (unit_it - 1) & 1);   // MMAs of the previous unit have read B
+      {
+        // features [K, C] (c contiguous) -> K-major 16-byte k-chunks per channel; 4 items (16 B each) per
+        // thread per round so 4*T global loads are in flight before the first conversion
+        const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
+        const int items = (p.Kp / kElemsPer16B) * p.c_tile;
+        constexpr int kBatch = 4;
+        for (int i0 = ctid; i0 < items; i0 += kTcComputeThreads * kBatch) {
+          float v[kBatch][kElemsPer16B];
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const int i = i0 + b * kTcComputeThreads;
+            const int kc = i / p.c_tile, c = i - kc * p.c_tile;
+            const int ch = c0 + c;
+#pragma unroll
+            for (int j = 0; j < kElemsPer16B; ++j) {
+              const int k = kc * kElemsPer16B + j;
+              v[b][j] = (i < items && k < p.K && ch < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch)) : 0.0f;
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < kBatch; ++b) {
+            const int i = i0 + b * kTcComputeThreads;
+            if (i >= items) break;
+            unsigned char* dst = b_smem + (size_t)i * 16;
+            if constexpr (kTf32) {
+              float hi[4], lo[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[b][j]); lo[j] = rna_tf32(v[b][j] - hi[j]); }
+              *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(dst + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            } else {
+              OT h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[b][j]);
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
+      mbar_arrive(&bars->b_full);
+      uint32_t any_general;   // barrier + OR-reduce: coef visible to all compute threads; does any blob need the slow form?
+      asm volatile(
+          "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+          "barrier.cta.red.or.pred r, 1, %2, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+          : "=r"(any_general) : "r"(my_general), "n"(kTcComputeThreads) : "memory");
+
+      // Two-level multiplicative suffix scan across blobs: each range is composited with a local
+      // transmittance; the back range is then scaled by the front range's total transmittance.
+      // The back range carries the extra rescale pass, so it gets the smaller share (7/16) of the blobs.
+#ifndef BS_SPLIT_NUM
+#define BS_SPLIT_NUM 7
+#endif
+      const int m_split = kHalves == 2 ? (((p.M * BS_SPLIT_NUM) >> 4) & ~3) : 0;   // multiple of 4: whole unrolled groups
+      const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
+      const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
+      OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
+      for (int t = 0; t < ntiles; ++t, ++tile_it) {
+        const int pix = (t_lo + t) * kTcTileM + px;
+        const bool live = pix < P;
+        const int y = live ? pix / p.W : 0;
+        const float xf = (float)(live ? pix - y * p.W : 0), yf = (float)y;
+        float* my = stash + px;
+        if constexpr (kFromScores) {
+          // stand-alone stage 3: this pixel's K weights come from global memory (plane-contiguous, coalesced
+          // across lanes for [N,K,H,W]); the two warps of a quarter split the planes
+          const OT* sc = reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn + (size_t)(live ? pix : 0) * p.sp;
+          const int k_split = kHalves == 2 ? (p.K >> 1) : 0;
+          const int k_lo = half ? 0 : k_split, k_hi = half ? k_split : p.K;
+          int k = k_lo;
+          for (; k + 8 <= k_hi; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)(k + j) * p.sk)) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) my[(size_t)(k + j) * kTcTileM] = v[j];
+          }
+          for (; k < k_hi; ++k) my[(size_t)k * kTcTileM] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)k * p.sk)) : 0.0f;
+          if (half == 0) {
+            for (int kk = p.K; kk < p.Kp; ++kk) my[(size_t)kk * kTcTileM] = 0.0f;
+          }
+        } else {
+          float T = 1.0f;
+          const bool wr = comp != nullptr && live;
+          const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
+          OT* const comp_px = comp + pix;                 // this pixel in plane 0; plane k is + k*P
+          int m = m_hi;
+          if (!any_general) {
+            // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
+            // transmittance T is a serial dependence (one FFMA per blob)
+            for (; m >= m_lo + 8; m -= 8) {
+              float s[8];
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
+  #pragma unroll
+              OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
+              for (int j = 0; j < 8; ++j) {
+                const float d = s[j] * T;
+                T = fmaf(-s[j], T, T);
+                my[(size_t)(m - j) * kTcTileM] = d;
+                if (wr_now) __stcs(cp - (ptrdiff_t)j * P, Cvt<OT>::from(d));
+              }
+            }
+          }
+          for (; m >= m_lo + 1; --m) {
+            const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
+            const float d = s * T;
+            T = fmaf(-s, T, T);
+            my[(size_t)m * kTcTileM] = d;
+            if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
+          }
+          if constexpr (kHalves == 2) {
+            if (half == 0) carry[px] = T;
+            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          }
+          if (half == kHalves - 1) {
+            float c = 1.0f;
+            if constexpr (kHalves == 2) {
+              c = carry[px];
+  #pragma unroll 4
+              for (int k = m_hi; k >= 1; --k) {
+                const float v = my[(size_t)k * kTcTileM] * c;
+                my[(size_t)k * kTcTileM] = v;
+                if (wr) __stcs(comp_px + (size_t)k * P, Cvt<OT>::from(v));
+              }
+            }
+            const float bg = T * c;                     // background: alpha 1 * total transmittance
+            my[0] = bg;
+            if (wr) __stcs(comp_px, Cvt<OT>::from(bg));
+          }
+          if (half == 0) {
+            for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
+          }
+        }
+        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
+
+        if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
+        tc_fence_after();
+        const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+        if constexpr (kTf32) {
+          for (int g = half; g < p.Kp / 8; g += kHalves) {  // the warps of a quarter interleave the k-groups
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float w = live ? my[(size_t)(g * 8 + j) * kTcTileM] : 0.0f;
+              const float h = rna_tf32(w);
+              hi[j] = __float_as_uint(h);
+              lo[j] = __float_as_uint(rna_tf32(w - h));
+            }
+            tmem_st8(tmem_a + lane_addr + g * 8, hi);
+            tmem_st8(tmem_a + lane_addr + a_cols + g * 8, lo);
+          }
+        } else {
+          // two k per 32-bit column (low half = even k): 8 columns = 16 consecutive k
+          for (int g = half; g < p.Kp / 16; g += kHalves) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float w0 = live ? my[(size_t)(g * 16 + 2 * j) * kTcTileM] : 0.0f;
+              const float w1 = live ? my[(size_t)(g * 16 + 2 * j + 1) * kTcTileM] : 0.0f;
+              OT lo16 = Cvt<OT>::from(w0), hi16 = Cvt<OT>::from(w1);
+              pk[j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo16)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi16)) << 16);
+            }
+            tmem_st8(tmem_a + lane_addr + g * 8, pk);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->a_full);
+        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+      }
+    } else if (warp < kTcComputeWarps + 4) {
+      // ========================================= epilogue ==========================================
+      const int q = warp - kTcComputeWarps;        // TMEM lane quarter
+      OT* out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
+      for (int t = 0; t < ntiles; ++t, ++tile_it) {
+        const int pix = (t_lo + t) * kTcTileM + q * 32 + lane;
+        const bool live = pix < P;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&bars->d_full[h], tile_it & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
+          OT* const o = out + (size_t)(h * c_half) * P + pix;   // this pixel in the half's first channel plane
+          const int ch_left = p.C - (c0 + h * c_half);          // valid channels in this half (may exceed c_half)
+          if (ch_left >= c_half && (c_half & 31) == 0) {
+            // fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
+            tmem_wait_ld();
+            for (int cc = 0; cc < c_half; cc += 64) {
+              if (cc + 32 < c_half) tmem_ld32(taddr + cc + 32, rb);
+              OT* oc = o + (size_t)cc * P;                       // chunk base; the 32 planes are immediates when kP > 0
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(ra[j])));
+              tmem_wait_ld();
+              if (cc + 32 < c_half) {
+                if (cc + 64 < c_half) tmem_ld32(taddr + cc + 64, ra);
+                oc += (size_t)32 * P;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(rb[j])));
+                tmem_wait_ld();
+              }
+            }
+          } else {
+            for (int cc = 0; cc < c_half; cc += 16) {           // c_half is a multiple of 16
+              uint32_t r[16];
+              tmem_ld16(taddr + cc, r);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (live && cc + j < ch_left) __stcs(o + (size_t)(cc + j) * P, Cvt<OT>::from(__uint_as_float(r[j])));
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bars->d_empty[h]);
+        }
+      }
+    } else {
+      // ========================================= MMA issue =========================================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<OT, __half>::value ? 0u : 1u), (uint32_t)c_half);
+        const uint32_t b_base = smem_u32(b_smem);
+        const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
+        mbar_wait(&bars->b_full, unit_it & 1);
+        for (int t = 0; t < ntiles; ++t, ++tile_it) {
+          mbar_wait(&bars->a_full, tile_it & 1);
+          tc_fence_after();
+          for (int h = 0; h < 2; ++h) {
+            if (tile_it > 0) mbar_wait(&bars->d_empty[h], (tile_it - 1) & 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem + (uint32_t)(h * c_half);
+            uint32_t acc = 0;
+            for (int ks = 0; ks < p.Kp / kKStep; ++ks) {
+              // descriptor of the [c_half x kKStep] slab: two 16-byte k-chunks, LBO apart
+              const uint32_t b_addr = b_base + (uint32_t)(2 * ks) * lbo + (uint32_t)(h * c_half) * 16u;
+              const uint64_t b_hi = make_b_desc(b_addr, lbo, sbo);
+              const uint32_t a_hi = tmem_a + (uint32_t)(ks * 8);
+              umma_ts<kTf32>(d_addr, a_hi, b_hi, idesc, acc);
+              acc = 1;
+              if constexpr (kTf32) {
+                const uint64_t b_lo = make_b_desc(b_addr + (uint32_t)b_bytes, lbo, sbo);
+                umma_ts<kTf32>(d_addr, a_hi, b_lo, idesc, 1u);
+                umma_ts<kTf32>(d_addr, a_hi + (uint32_t)a_cols, b_hi, idesc, 1u);
+              }
+            }
+            tc_commit(&bars->d_full[h]);
+          }
+          tc_commit(&bars->a_free);
+        }
+        tc_commit(&bars->b_free);
+      }
+      __syncwarp();
+    }
+  }
+
+  // the last commits arrive asynchronously: see them land before the CTA (and its smem barriers) goes away
+  if (warp == kTcMmaWarp && lane == 0 && tile_it > 0) {
+    mbar_wait(&bars->a_free, (tile_it - 1) & 1);
+    mbar_wait(&bars->b_free, (unit_it - 1) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kTcMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+
+// ---- host side ---------------------------------------------------------------------------------------
+static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct TcPlan { int Kp, c_tile; size_t smem; bool ok; const char* why; };
+
+static inline TcPlan plan_tc(int K, int C, bool tf32) {
+  TcPlan pl{};
+  pl.ok = false;
+  const int kstep = tf32 ? 8 : 16;
+  pl.Kp = round_up(K, kstep);
+  if (K - 1 > kTcMaxBlobs) { pl.why = "more than 127 blobs: use the FMA engine"; return pl; }
+  if (C % 32 != 0) { pl.why = "C must be a multiple of 32 for the tensor-core render"; return pl; }
+  const int a_cols = tf32 ? 2 * pl.Kp : pl.Kp / 2;
+  const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : 2);                  // B bytes per channel (hi+lo fp32 | 16-bit)
+  const size_t fixed = (size_t)pl.Kp * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
+  int c_tile = std::min(kTcMaxCTile, C);
+  c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
+  c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
+  if (c_tile < 32) { pl.why = "K too large for shared/tensor memory"; return pl; }
+  // prefer a tile that divides C (no ragged chunk)
+  for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
+    if (C % c == 0) { c_tile = c; break; }
+  pl.c_tile = c_tile;
+  pl.smem = fixed + per_c * c_tile;
+  pl.ok = true;
+  return pl;
+}
+
+// Fill the shape / work-unit fields shared by both A sources.
+static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int H, int W, int C) {
+  p.N = N; p.M = K - 1; p.H = H; p.W = W; p.C = C; p.K = K; p.Kp = pl.Kp;
+  p.c_tile = pl.c_tile; p.c_chunks = (C + pl.c_tile - 1) / pl.c_tile;
+  const int P = H * W;
+  p.tiles_per_image = (P + kTcTileM - 1) / kTcTileM;
+  // Work units: whole images when there are plenty; otherwise split each image's tiles so that every SM gets work.
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long base_units = (long long)N * p.c_chunks;
+  int segs = 1;
+  if (base_units < 4ll * sms) {
+    segs = (int)std::min<long long>(p.tiles_per_image, (4ll * sms + base_units - 1) / base_units);
+    if (p.tiles_per_image / segs < 4) segs = std::max(1, p.tiles_per_image / 4);   // keep >= 4 tiles per B load
+  }
+  p.tiles_per_unit = (p.tiles_per_image + segs - 1) / segs;
+  p.segs = (p.tiles_per_image + p.tiles_per_unit - 1) / p.tiles_per_unit;
+  const long long total = base_units * p.segs;
+  if (total > 0x7fffffffll) BS_UNSUPPORTED("too many work units");
+  p.total_units = (int)total;
+  return 0;
+}
+
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
+static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  BS_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured_dev = dev;
+  }
+  static thread_local int sm_count = 0, sm_dev = -1;
+  if (sm_dev != dev) {
+    BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    sm_dev = dev;
+  }
+  const int grid = std::min(sm_count, p.total_units);
+  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(p);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename FT, typename OT, bool kTf32, int kHalves, bool kFromScores>
+static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
+  if constexpr (kHalves == 2) {   // plane-stride specialisations for BlobNet's latent resolutions (64/32/16)
+    switch (p.H * p.W) {
+      case 4096: return launch_tc_p<FT, OT, kTf32, kHalves, 4096, kFromScores>(p, smem, st);
+      case 1024: return launch_tc_p<FT, OT, kTf32, kHalves, 1024, kFromScores>(p, smem, st);
+      case 256: return launch_tc_p<FT, OT, kTf32, kHalves, 256, kFromScores>(p, smem, st);
+    }
+  }
+  return launch_tc_p<FT, OT, kTf32, kHalves, 0, kFromScores>(p, smem, st);
+}
+
+// 8 compute warps (kHalves = 2) win for every dtype once the GPU settles at its sustained clocks
+// (profiles/ab_compute_warps_r1.txt); BLOBSPLAT_TC_HALVES=1|2 overrides the choice (A/B knob, read per call).
+template <bool kFromScores>
+static int launch_tc_dtype(const RenderTcParams& p, size_t smem, int out_dtype, cudaStream_t st) {
+  int halves = 2;
+  if (!kFromScores) {
+    if (const char* e = getenv("BLOBSPLAT_TC_HALVES")) { if (e[0] == '1') halves = 1; }
+  }
+  if (out_dtype == BLOBSPLAT_F32) {
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<float, float, true, 1, kFromScores>(p, smem, st); }
+    return launch_tc<float, float, true, 2, kFromScores>(p, smem, st);
+  }
+  if (out_dtype == BLOBSPLAT_BF16) {
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__nv_bfloat16, __nv_bfloat16, false, 1, kFromScores>(p, smem, st); }
+    return launch_tc<__nv_bfloat16, __nv_bfloat16, false, 2, kFromScores>(p, smem, st);
+  }
+  if (out_dtype == BLOBSPLAT_F16) {
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__half, __half, false, 1, kFromScores>(p, smem, st); }
+    return launch_tc<__half, __half, false, 2, kFromScores>(p, smem, st);
+  }
+  BS_UNSUPPORTED("tensor-core engine: unsupported dtype %d", out_dtype);
+}
+
+}  // namespace blobsplat

@@ -223,11 +223,24 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
     """
     if not level_features:
         raise ValueError("level_features is empty")
-    d, _ = ops.render_scores(xs, ys, covs, sizes, score_size, score_size, out_dtype=out_dtype)
-    pyr = pyramid_resize(d, cutoff=min(level_features))
     grids = {}
+    d = None
+    top = level_features.get(score_size)
+    if top is not None and engine != "fma" and covs.dtype != torch.float64:
+        # the full-resolution level comes out of the fused render (stages 1+2+3 in one launch)
+        try:
+            d, grids[score_size] = ops.render_fused(xs, ys, covs, sizes, top, score_size, score_size,
+                                                    out_dtype=out_dtype or covs.dtype)
+        except C.BlobSplatError:
+            if engine == "tensor":
+                raise
+            d = None
+    if d is None:
+        d, _ = ops.render_scores(xs, ys, covs, sizes, score_size, score_size, out_dtype=out_dtype)
+    pyr = pyramid_resize(d, cutoff=min(level_features))
     for s, f in level_features.items():
-        grids[s] = splat_features_from_scores(pyr[s], f.to(d.dtype), s, channels_last=False, engine=engine)
+        if s not in grids:
+            grids[s] = splat_features_from_scores(pyr[s], f.to(d.dtype), s, channels_last=False, engine=engine)
     return {"scores_pyramid": pyr, "feature_grids": grids}
 
 

@@ -139,6 +139,9 @@ BLOBSPLAT_API int blobsplat_pyramid(const void* in, void* const* outs, int n_lev
  *   scores: element strides (in elements) stride_n, stride_k, stride_p with pixel p = y*W + x
  *           ([N,K,H,W] contiguous: K*P, P, 1;  [N,H,W,K] contiguous: P*K, 1, K)
  *   features [N, K, C] contiguous, same dtype as scores and out.
+ *   engine: AUTO runs the contraction on tcgen05 tensor cores when it is a real dense one (K >= 12, C >= 64,
+ *           C % 32 == 0, K <= 128, not float64; float32 uses the 3xTF32 split) and on CUDA-core FMA tiles
+ *           otherwise; FMA / TENSOR force one (TENSOR fails with BLOBSPLAT_E_UNSUPPORTED outside its envelope).
  */
 BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride_k, int64_t stride_p,
                             const void* features, void* out, int N, int K, int C, int H, int W,

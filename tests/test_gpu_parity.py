@@ -315,3 +315,41 @@ def test_custom_viz_score_fn_branch():
     want = blob_oracle.splat_features(**syn, score_size=16, interp_size=16, viz_size=16, is_viz=True, only_vis=True,
                                       viz_score_fn=fn_n, viz_colors=blob_oracle.BLOB_VIS_COLORS, dtype=np.float64)
     close_scaled(_np(got["feature_img"]), want["feature_img"], 1e-5, "custom viz")
+
+
+@pytest.mark.parametrize("n,k,s,c,dtype,rel", [
+    (3, 33, 64, 320, torch.float32, 1e-5), (2, 33, 32, 640, torch.float32, 1e-5), (2, 33, 8, 1280, torch.float32, 1e-5),
+    (2, 65, 16, 1280, torch.bfloat16, 1e-2), (4, 17, 24, 96, torch.float16, 2e-3), (1, 128, 20, 64, torch.float32, 1e-5),
+    (2, 12, 64, 64, torch.float32, 1e-5)])
+def test_stage3_tensor_engine_vs_oracle(n, k, s, c, dtype, rel):
+    """splat_features_from_scores on the tcgen05 engine (weights loaded from score maps into TMEM), both layouts,
+    against the float64 oracle and against the FMA engine."""
+    U = _impl()
+    g = torch.Generator().manual_seed(n * 1000 + k)
+    sc = torch.rand(n, k, s, s, generator=g)
+    sc = sc / sc.sum(1, keepdim=True)                                   # convex weights like composed scores
+    ft = torch.randn(n, k, c, generator=g)
+    sc_d, ft_d = sc.to(DEV).to(dtype), ft.to(DEV).to(dtype)
+    want = blob_oracle.splat_features_from_scores(_np(sc_d).astype(np.float64), _np(ft_d).astype(np.float64), s,
+                                                  channels_last=False)
+    got_t = U.splat_features_from_scores(sc_d, ft_d, s, channels_last=False, engine="tensor")
+    got_f = U.splat_features_from_scores(sc_d, ft_d, s, channels_last=False, engine="fma")
+    assert got_t.shape == (n, c, s, s) and got_t.dtype == dtype and got_t.is_contiguous()
+    close_scaled(_np(got_t), want, rel, "tensor engine")
+    close_scaled(_np(got_f), want, rel, "fma engine")
+    nhwk = sc_d.permute(0, 2, 3, 1).contiguous()                        # true channels-last storage (strided planes)
+    got_cl = U.splat_features_from_scores(nhwk, ft_d, s, channels_last=True, engine="tensor")
+    close_scaled(_np(got_cl), want, rel, "tensor engine, NHWK")
+    auto = U.splat_features_from_scores(sc_d, ft_d, s, channels_last=False)
+    close_scaled(_np(auto), want, rel, "auto engine")
+
+
+def test_tensor_engine_rejects_outside_envelope():
+    U = _impl()
+    from blobctrl_b200 import _capi
+    sc = torch.rand(1, 5, 8, 8, device=DEV); ft = torch.randn(1, 5, 30, device=DEV)
+    with pytest.raises(_capi.BlobSplatError):                           # C % 32 != 0
+        U.splat_features_from_scores(sc, ft, 8, channels_last=False, engine="tensor")
+    out = U.splat_features_from_scores(sc, ft, 8, channels_last=False)  # auto -> FMA
+    want = torch.einsum("nkhw,nkc->nchw", sc, ft)
+    assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item()
