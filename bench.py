@@ -12,8 +12,9 @@ that batch through the public API: blob parameters + features -> composed score 
 feature grid [N,320,64,64].
 
   value      whole-job Mpixel*blob/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e        same metric through the same public call with HOST (pinned) inputs: H2D of parameters and
-             features and a D2H read-back of the last image's maps inside the timed region
+  e2e        same metric through the public host-input API (blobctrl_b200.streaming.HostRenderer) with HOST
+             (pinned) inputs: chunked H2D of parameters and features overlapped with the render, and a D2H
+             read-back of the last image's maps, all inside the timed region
   roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs MEASURED_PEAKS hbm_gbs
   cpu_baseline  the reference's PyTorch-CPU op sequence (oracle/aten_port.py — /root/reference cannot
              travel to the GPU box) timed on the host cores on a bounded sample of the same workload
@@ -78,7 +79,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -228,17 +229,18 @@ def main():
     del out
 
     # ---- per-kernel durations (CUDA events between the launches of one step) -----------------------
-    kern = probe_kernels(ops, blobs, feats, dev, max(args.steps // 2, 5))
-
     with ClockSampler(local) as clk:
+        kern = probe_kernels(ops, blobs, feats, dev, max(args.steps // 2, 5))
         total = time_steps(step, args.steps, args.warmup, barrier)
         # ---- e2e: host (pinned) inputs in, last image's maps out, inside the timed region ----------
         out_host = torch.empty((M_BLOBS + 1 + CHANNELS, SIZE, SIZE), dtype=torch.float32).pin_memory()
 
+        from blobctrl_b200.streaming import HostRenderer
+        host_renderer = HostRenderer(N_IMG, M_BLOBS, SIZE, CHANNELS, torch.float32, dev, chunks=8)
+
         def e2e_step():
-            b = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-            f = pin_feats.to(dev, non_blocking=True)
-            o = B.splat_features(**b, features=f, score_size=SIZE, interp_size=SIZE, ret_layout=False)
+            # public host-input API: chunked H2D on a copy stream overlapped with the fused render
+            o = host_renderer(pin["xs"], pin["ys"], pin["covs"], pin["sizes"], pin_feats)
             out_host[:M_BLOBS + 1].copy_(o["scores_pyramid"][SIZE][-1], non_blocking=True)
             out_host[M_BLOBS + 1:].copy_(o["feature_grid"][-1], non_blocking=True)
 
@@ -276,9 +278,9 @@ def main():
             line["variants"] = variants(B, ops, dev, peak)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            best, med, times = cpu_reference_rate(32, 6, threads)
+            best, med, times = cpu_reference_rate(128, 6, threads)
             line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port", "median": med,
-                                    "sample": f"32 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
+                                    "sample": f"128 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
                                               f"best of 6 after 1 warm-up, {sum(times):.1f} s CPU wall"}
             b1, _, t1 = cpu_reference_rate(8, 3, 1)
             line["cpu_baseline"]["single_thread"] = {"value": b1, "cores": 1, "sample": "8 images, best of 3"}

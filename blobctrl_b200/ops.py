@@ -182,3 +182,21 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
                                      C.dtype_code(f.dtype), n, m, height, width, c, C.ptr(composed), C.ptr(grid),
                                      C.dtype_code(out_dtype), C.dev_of(covs_c), C.stream_of(covs_c)))
     return composed, grid
+
+
+def render_fused_into(xs, ys, covs, sizes, features, height: int, width: int, composed: Optional[torch.Tensor],
+                      grid: torch.Tensor) -> None:
+    """blobsplat_render into caller-owned (contiguous) output buffers; inputs must already be dense float32 [N,M]
+    device tensors (no canonicalisation, no allocation: usable under CUDA-graph capture and in copy pipelines)."""
+    n, m = covs.shape[0], covs.shape[1]
+    c = features.shape[2]
+    for t in (xs, ys, covs, sizes, features, grid) + ((composed,) if composed is not None else ()):
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("render_fused_into needs contiguous CUDA tensors")
+    if grid.shape != (n, c, height, width) or (composed is not None and composed.shape != (n, m + 1, height, width)):
+        raise RuntimeError("output buffer shape mismatch")
+    if features.dtype != grid.dtype or (composed is not None and composed.dtype != grid.dtype):
+        raise RuntimeError("features, composed and grid must share a dtype")
+    C.check(C.lib().blobsplat_render(C.ptr(xs), C.ptr(ys), C.ptr(covs), C.ptr(sizes), C.ptr(features),
+                                     C.dtype_code(features.dtype), n, m, height, width, c, C.ptr(composed), C.ptr(grid),
+                                     C.dtype_code(grid.dtype), C.dev_of(grid), C.stream_of(grid)))

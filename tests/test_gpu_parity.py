@@ -353,3 +353,20 @@ def test_tensor_engine_rejects_outside_envelope():
     out = U.splat_features_from_scores(sc, ft, 8, channels_last=False)  # auto -> FMA
     want = torch.einsum("nkhw,nkc->nchw", sc, ft)
     assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+def test_host_renderer_chunked_copy_matches_single_call():
+    """blobctrl_b200.streaming: chunked H2D overlapped with the render == one splat_features call (images are
+    independent), repeated calls reuse the buffers safely."""
+    from blobctrl_b200.streaming import HostRenderer
+    U = _impl()
+    n, m, s, c = 37, 16, 32, 64
+    r = HostRenderer(n, m, s, c, torch.float32, DEV, chunks=5)
+    for seed in (21, 22):
+        syn = blob_oracle.synthetic_blobs(n, m, seed=seed, c=c)
+        host = {k: torch.from_numpy(v).pin_memory() for k, v in syn.items()}
+        out = r(host["xs"], host["ys"], host["covs"], host["sizes"], host["features"])
+        ref = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=s, interp_size=s, ret_layout=False)
+        torch.cuda.synchronize()
+        assert torch.equal(out["scores_pyramid"][s], ref["scores_pyramid"][s])
+        assert torch.equal(out["feature_grid"], ref["feature_grid"])
