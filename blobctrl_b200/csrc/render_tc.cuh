@@ -344,10 +344,10 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             // transmittance T is a serial dependence (one FFMA per blob)
             for (; m >= m_lo + 8; m -= 8) {
               float s[8];
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
-  #pragma unroll
               OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
+#pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float d = s[j] * T;
                 T = fmaf(-s[j], T, T);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             float c = 1.0f;
             if constexpr (kHalves == 2) {
               c = carry[px];
-  #pragma unroll 4
+#pragma unroll 4
               for (int k = m_hi; k >= 1; --k) {
                 const float v = my[(size_t)k * kTcTileM] * c;
                 my[(size_t)k * kTcTileM] = v;

@@ -18,9 +18,9 @@ blobs, feats = synthetic(1024, 64, 320, seed=0)
 b = {k: v.cuda() for k, v in blobs.items()}
 for dtype in (torch.float32, torch.bfloat16):
     f = feats.cuda().to(dtype)
-    res = {"1": [], "2": []}
+    res = {"1": [], "2": [], "4": []}
     for rnd in range(4):
-        for h in ("1", "2"):
+        for h in ("1", "2", "4"):
             os.environ["BLOBSPLAT_TC_HALVES"] = h
             res[h].append(t(lambda: ops.render_fused(**b, features=f, height=64, width=64, out_dtype=dtype)))
     print(dtype, {h: [round(x, 4) for x in v] for h, v in res.items()})

@@ -55,6 +55,16 @@ def run():
                 res[n].append(round(e0.elapsed_time(e1) / 20, 4))
         print(dtype)
         for n, v in res.items(): print(f"  {n:18s} {v}  median {sorted(v)[len(v)//2]}")
+        for tn in [n for n in libs if n.startswith("timing")]:
+            call(libs[tn]); torch.cuda.synchronize()
+            buf = (ctypes.c_ulonglong * 48)()
+            libs[tn].blobsplat_debug_timing(buf)
+            print(" ", tn)
+            names = {0: "compute front (warp0)", 1: "compute back (warp4)", 2: "epilogue (first warp)", 3: "MMA warp"}
+            for role in range(4):
+                row = [buf[role * 12 + i] for i in range(12)]
+                tot = sum(row) or 1
+                print(f"  timing {names[role]:24s} total {tot/1e3:.0f}k cyc:", [f"{i}:{100*v/tot:.0f}%" for i, v in enumerate(row) if v])
 
 if __name__ == "__main__":
     build() if sys.argv[1:2] == ["build"] else run()
