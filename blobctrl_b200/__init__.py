@@ -7,8 +7,8 @@ Nothing else of BlobCtrl (BlobNet, UNet, diffusers, the Gradio app) is reimpleme
 """
 from . import _capi
 from .utils.utils import (BLOB_VIS_COLORS, pyramid_resize, splat_features, splat_features_from_scores,
-                          splat_features_multiscale, visualize_features, viz_score_fn)
+                          splat_ellipses, splat_features_multiscale, visualize_features, viz_score_fn)
 
 __version__ = "0.1.0"
 __all__ = ["splat_features", "splat_features_from_scores", "pyramid_resize", "visualize_features",
-           "splat_features_multiscale", "viz_score_fn", "BLOB_VIS_COLORS", "_capi"]
+           "splat_features_multiscale", "splat_ellipses", "viz_score_fn", "BLOB_VIS_COLORS", "_capi"]

@@ -43,6 +43,7 @@ SIGNATURES = {
     "blobsplat_get_caps": [ctypes.POINTER(Caps)],
     "blobsplat_last_error": [ctypes.c_char_p, ctypes.c_size_t],
     "blobsplat_scores": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
+    "blobsplat_scores_ellipse": [_P, _P, ctypes.c_float, ctypes.c_float, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P],
     "blobsplat_composite": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_resize_bilinear": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_pyramid": [_P, ctypes.POINTER(_P), _I, _I, _I, _I, _I, _P],

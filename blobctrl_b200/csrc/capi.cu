@@ -24,6 +24,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 int scores_dispatch(const void*, const void*, const void*, const float*, int, int, int, int, int, int, void*, int,
                     void*, int, int, cudaStream_t);
 int composite_dispatch(const void*, void*, int, int, int, int, int, cudaStream_t);
+int scores_ellipse_dispatch(const float*, const float*, float, float, int, int, int, int, int, void*, int, void*, int,
+                            cudaStream_t);
 int resize_dispatch(const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int pyramid_dispatch(const void*, void* const*, int, int, int, int, cudaStream_t);
 int feature_splat_fma_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int,
@@ -85,6 +87,24 @@ int blobsplat_scores(const void* xs, const void* ys, const void* covs, const flo
   if (g.status) return g.status;
   return scores_dispatch(xs, ys, covs, sizes, param_dtype, N, M, H, W, select, composed, composed_dtype, raw,
                          raw_dtype, composite_mode, (cudaStream_t)stream);
+}
+
+int blobsplat_scores_ellipse(const float* ellipses, const float* sizes, float img_w, float img_h, int N, int M, int H,
+                             int W, int select, void* composed, int composed_dtype, void* raw, int raw_dtype, int device,
+                             void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1, "bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+  BS_CHECK_ARG(M <= kMaxBlobs && N <= 65535 && (long long)H * W < (1ll << 31), "shape too large");
+  BS_CHECK_ARG(img_w > 0.f && img_h > 0.f, "bad image size %g x %g", (double)img_w, (double)img_h);
+  BS_CHECK_ARG(select >= BLOBSPLAT_SELECT_ALL && select <= BLOBSPLAT_SELECT_BG, "bad select %d", select);
+  BS_CHECK_ARG(composed || raw, "both outputs are NULL");
+  BS_CHECK_ARG(!composed || valid_dtype(composed_dtype), "bad composed dtype %d", composed_dtype);
+  BS_CHECK_ARG(!raw || valid_dtype(raw_dtype), "bad raw dtype %d", raw_dtype);
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(M == 0 || (ellipses && sizes), "NULL ellipse parameter pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return scores_ellipse_dispatch(ellipses, sizes, img_w, img_h, N, M, H, W, select, composed, composed_dtype, raw, raw_dtype,
+                                 (cudaStream_t)stream);
 }
 
 int blobsplat_composite(const void* scores_in, void* composed, int N, int K, int H, int W, int dtype, int device,

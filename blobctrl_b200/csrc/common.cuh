@@ -180,6 +180,33 @@ __device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double 
   return o;
 }
 
+// Same coefficients straight from an OpenCV ellipse ((xc,yc),(d1,d2),angle_deg) in pixels of an img_w x img_h image
+// — the reference's host recipe (scripts/blobctrl_inference.py:71-109 + utils.py:297-341) folded into the per-blob
+// prologue: theta = rad(((180-angle) mod 180 + 90) mod 180), Sigma = Q diag(b^2, a^2) Q^T / (img_w^2 + img_h^2) with
+// Q = [[c, s], [-s, c]] (the rotation with the off-diagonals negated), a = d1/2, b = d2/2.  Then
+// q = D^2 * ((c*dx' - s*dy')^2 / b^2 + (s*dx' + c*dy')^2 / a^2), dx' = dx/W, dy' = dy/H: no covariance, no inverse, no
+// cancellation — exact whitening factors even for the degenerate 1e-5-pixel ellipses of the demo states.
+__device__ __forceinline__ BlobCoef make_blob_coef_ellipse(double xc, double yc, double d1, double d2, double angle_deg,
+                                                           float size, double img_w, double img_h, int H, int W) {
+  BlobCoef o;
+  const double cx = xc / img_w * (double)W, cy = yc / img_h * (double)H;
+  o.cx_hi = (float)cx; o.cx_lo = (float)(cx - (double)o.cx_hi);
+  o.cy_hi = (float)cy; o.cy_lo = (float)(cy - (double)o.cy_hi);
+  double a1 = 180.0 - angle_deg; a1 -= 180.0 * floor(a1 / 180.0);            // python's % 180
+  double a2 = a1 + 90.0; a2 -= 180.0 * floor(a2 / 180.0);
+  const double th = a2 * 0.017453292519943295;
+  const double cs = cos(th), sn = sin(th);
+  const double a = 0.5 * d1, b = 0.5 * d2;
+  const double D = sqrt((img_w * img_w + img_h * img_h) * 1.4426950408889634);  // diagonal, log2(e) folded in
+  const double m00 = D * cs / (b * (double)W), m01 = -D * sn / (b * (double)H);
+  const double m10 = D * sn / (a * (double)W), m11 = D * cs / (a * (double)H);
+  const double Bq = m00 * m01 + m10 * m11, Cq = m01 * m01 + m11 * m11;
+  const double t = sqrt(Cq);
+  o.t = (float)t; o.r = (float)(Bq / t); o.p = (float)(fabs(m00 * m11 - m01 * m10) / t);
+  o.flags = (size < 0.5f) ? kGated : 0u;
+  return o;
+}
+
 // s = min(1, 2*sigmoid(-q)) = min(1, 2 / (1 + 2^(q*log2e)))   (utils.py:162-163)
 __device__ __forceinline__ float opacity_from_q2(float q2) {
   float e;

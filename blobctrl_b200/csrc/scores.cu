@@ -32,7 +32,8 @@ template <typename O, int V>
 __global__ void __launch_bounds__(kScoreThreads)
 scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys,
                       const float* __restrict__ covs, const float* __restrict__ sizes, int M, int H, int W,
-                      int select, int ksel, O* __restrict__ composed, O* __restrict__ raw) {
+                      int select, int ksel, O* __restrict__ composed, O* __restrict__ raw,
+                      const float* __restrict__ ell, float img_w, float img_h) {
   __shared__ BlobCoef coef[kBlobChunk];
   const int n = blockIdx.y;
   const int P = H * W;
@@ -55,9 +56,15 @@ scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += kScoreThreads) {
       const size_t b = (size_t)n * M + lo + i;
-      const float* c = covs + 4 * b;
-      coef[i] = make_blob_coef((double)xs[b], (double)ys[b], (double)c[0], (double)c[1], (double)c[2],
-                               (double)c[3], sizes[b], H, W);
+      if (ell != nullptr) {   // ellipse front end: xs/ys/covs unused
+        const float* e = ell + 5 * b;
+        coef[i] = make_blob_coef_ellipse((double)e[0], (double)e[1], (double)e[2], (double)e[3], (double)e[4], sizes[b],
+                                         (double)img_w, (double)img_h, H, W);
+      } else {
+        const float* c = covs + 4 * b;
+        coef[i] = make_blob_coef((double)xs[b], (double)ys[b], (double)c[0], (double)c[1], (double)c[2],
+                                 (double)c[3], sizes[b], H, W);
+      }
     }
     __syncthreads();
     if (!active) continue;
@@ -268,7 +275,7 @@ composite_kernel(const T* __restrict__ in, T* __restrict__ out, int K, int P) {
 template <typename O>
 static int launch_lane_pixel_f32(const float* xs, const float* ys, const float* covs, const float* sizes, int N,
                                  int M, int H, int W, int select, int ksel, void* composed, void* raw,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, const float* ell = nullptr, float img_w = 0.f, float img_h = 0.f) {
   constexpr int VMAX = Vec128<O>::n;
   const int P = H * W;
   const bool vec = (W % VMAX == 0) && aligned_to(composed, 16) && aligned_to(raw, 16);
@@ -276,10 +283,10 @@ static int launch_lane_pixel_f32(const float* xs, const float* ys, const float* 
   dim3 grid((unsigned)((P / V + kScoreThreads - 1) / kScoreThreads), (unsigned)N);
   if (vec)
     scores_lane_pixel_f32<O, VMAX><<<grid, kScoreThreads, 0, st>>>(xs, ys, covs, sizes, M, H, W, select, ksel,
-                                                                  (O*)composed, (O*)raw);
+                                                                  (O*)composed, (O*)raw, ell, img_w, img_h);
   else
     scores_lane_pixel_f32<O, 1><<<grid, kScoreThreads, 0, st>>>(xs, ys, covs, sizes, M, H, W, select, ksel,
-                                                               (O*)composed, (O*)raw);
+                                                               (O*)composed, (O*)raw, ell, img_w, img_h);
   BS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -351,6 +358,19 @@ int scores_dispatch(const void* xs, const void* ys, const void* covs, const floa
     case BLOBSPLAT_F16: return launch_lane_pixel_f32<__half>(fx, fy, fc, sizes, N, M, H, W, select, ksel, composed, raw, st);
   }
   BS_UNSUPPORTED("unknown output dtype %d", odt);
+}
+
+int scores_ellipse_dispatch(const float* ell, const float* sizes, float img_w, float img_h, int N, int M, int H, int W,
+                            int select, void* composed, int composed_dtype, void* raw, int raw_dtype, cudaStream_t st) {
+  const int ksel = select == BLOBSPLAT_SELECT_ALL ? M + 1 : (select == BLOBSPLAT_SELECT_FG ? M : 1);
+  if (composed && raw && composed_dtype != raw_dtype) BS_UNSUPPORTED("composed and raw maps must share a dtype");
+  const int odt = composed ? composed_dtype : raw_dtype;
+  switch (odt) {
+    case BLOBSPLAT_F32: return launch_lane_pixel_f32<float>(nullptr, nullptr, nullptr, sizes, N, M, H, W, select, ksel, composed, raw, st, ell, img_w, img_h);
+    case BLOBSPLAT_BF16: return launch_lane_pixel_f32<__nv_bfloat16>(nullptr, nullptr, nullptr, sizes, N, M, H, W, select, ksel, composed, raw, st, ell, img_w, img_h);
+    case BLOBSPLAT_F16: return launch_lane_pixel_f32<__half>(nullptr, nullptr, nullptr, sizes, N, M, H, W, select, ksel, composed, raw, st, ell, img_w, img_h);
+  }
+  BS_UNSUPPORTED("ellipse front end renders float32/bfloat16/float16 maps (got dtype %d)", odt);
 }
 
 int composite_dispatch(const void* in, void* out, int N, int K, int H, int W, int dtype, cudaStream_t st) {

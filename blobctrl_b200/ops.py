@@ -200,3 +200,28 @@ def render_fused_into(xs, ys, covs, sizes, features, height: int, width: int, co
     C.check(C.lib().blobsplat_render(C.ptr(xs), C.ptr(ys), C.ptr(covs), C.ptr(sizes), C.ptr(features),
                                      C.dtype_code(features.dtype), n, m, height, width, c, C.ptr(composed), C.ptr(grid),
                                      C.dtype_code(grid.dtype), C.dev_of(grid), C.stream_of(grid)))
+
+
+def render_scores_from_ellipses(ellipses: torch.Tensor, sizes: Optional[torch.Tensor], image_size: Tuple[int, int],
+                                height: int, width: int, select: str = "all", want_raw: bool = False,
+                                out_dtype: torch.dtype = torch.float32):
+    """Stages 1+2 straight from OpenCV ellipses (blobsplat_scores_ellipse).
+
+    ellipses: [N, M, 5] (xc, yc, d1, d2, angle_deg) in pixels of an image of ``image_size`` = (img_h, img_w);
+    sizes: [N, M] existence flags or None (all blobs exist).  Returns (composed [N,Ksel,H,W], raw | None)."""
+    C.require_cuda(ellipses, "ellipses")
+    if ellipses.ndim != 3 or ellipses.shape[-1] != 5:
+        raise RuntimeError(f"ellipses must be [N, M, 5], got {tuple(ellipses.shape)}")
+    n, m = ellipses.shape[:2]
+    e = ellipses.to(torch.float32).contiguous()
+    sz = torch.ones((n, m), dtype=torch.float32, device=e.device) if sizes is None else \
+        torch.as_tensor(sizes, device=e.device).to(torch.float32).reshape(n, m).contiguous()
+    img_h, img_w = image_size
+    ksel = {"all": m + 1, "fg": m, "bg": 1}[select]
+    composed = torch.empty((n, ksel, height, width), dtype=out_dtype, device=e.device)
+    raw = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=e.device) if want_raw else None
+    oc = C.dtype_code(out_dtype)
+    C.check(C.lib().blobsplat_scores_ellipse(C.ptr(e), C.ptr(sz), float(img_w), float(img_h), n, m, height, width,
+                                             _SELECT[select], C.ptr(composed), oc, C.ptr(raw), oc, C.dev_of(e),
+                                             C.stream_of(e)))
+    return composed, raw

@@ -244,6 +244,34 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
     return {"scores_pyramid": pyr, "feature_grids": grids}
 
 
+def splat_ellipses(ellipses, sizes=None, image_size=(512, 512), score_size=64, only_splatting_fg=False,
+                   only_splatting_bg=False, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """Device-side ellipse front end: the whole host recipe of the reference's callers —
+    get_gs_from_ellipse -> normalize_gs -> get_blob_dict_from_norm_gs -> splat_features(return_d_score=True)
+    (scripts/blobctrl_inference.py:71-117) — for a batch, in one launch.
+
+    ellipses: [N, M, 5] tensor (or nested list) of (xc, yc, d1, d2, angle_deg), cv2.fitEllipse convention, in pixels
+    of an ``image_size`` = (height, width) image; blob index = depth order (highest in front).
+    score_size: int S or (H, W).  Returns composed maps [N, M+1 | M | 1, H, W] (float32 / bfloat16 / float16).
+    """
+    e = torch.as_tensor(ellipses, dtype=torch.float32)
+    if e.ndim == 1:
+        e = e.view(1, 1, 5)
+    elif e.ndim == 2:
+        e = e.unsqueeze(0)
+    if not e.is_cuda:
+        e = e.cuda()                       # a few floats per blob: the host->device hop of the parameters
+    h, w = (score_size, score_size) if isinstance(score_size, int) else score_size
+    select = "bg" if only_splatting_bg else ("fg" if only_splatting_fg else "all")
+    return ops.render_scores_from_ellipses(e, sizes, image_size, int(h), int(w), select=select, out_dtype=out_dtype)[0]
+
+
+def flatten_cv_ellipse(ellipse):
+    """((xc, yc), (d1, d2), angle) -> [xc, yc, d1, d2, angle] (the layout splat_ellipses takes)."""
+    (xc, yc), (d1, d2), ang = ellipse
+    return [float(xc), float(yc), float(d1), float(d2), float(ang)]
+
+
 # --------------------------------------------------------------------------------------------------
 # geometry (host side, float64) — the input contract of the renderer
 # --------------------------------------------------------------------------------------------------

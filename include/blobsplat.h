@@ -110,6 +110,19 @@ BLOBSPLAT_API int blobsplat_scores(const void* xs, const void* ys, const void* c
                      int composite_mode, int device, void* stream);
 
 /*
+ * (1a) scores from ellipses — the device-side front end.  Same maps as (1), but the blobs are
+ *      given as OpenCV-convention ellipses instead of (centre, covariance): replaces the host recipe
+ *      get_gs_from_ellipse -> normalize_gs -> get_blob_dict_from_norm_gs (scripts/blobctrl_inference.py:71-109, same
+ *      code at scripts/blobctrl_app.py:604-629; ellipse_to_gaussian at blobctrl/utils/utils.py:297-341) plus (1).
+ *   ellipses [N, M, 5] float32: xc, yc, d1, d2 in pixels of an img_w x img_h image; angle in degrees
+ *            (cv2.fitEllipse convention).  sizes [N, M] as in (1).  Blob index = depth order (highest in front).
+ */
+BLOBSPLAT_API int blobsplat_scores_ellipse(const float* ellipses, const float* sizes, float img_w, float img_h,
+                             int N, int M, int H, int W, int select,
+                             void* composed, int composed_dtype, void* raw, int raw_dtype,
+                             int device, void* stream);
+
+/*
  * (1b) composite only.  Replaces utils.py:179-181 / :205-206 applied to caller-modified raw scores
  *      (the `viz_score_fn` branch).  scores_in / composed: planar [N, K, H, W], same dtype.
  */

@@ -23,7 +23,7 @@ def _declared():
 def test_header_declares_the_expected_entry_points():
     d = _declared()
     assert set(d) == {"blobsplat_abi_version", "blobsplat_get_caps", "blobsplat_last_error", "blobsplat_scores",
-                      "blobsplat_composite", "blobsplat_resize_bilinear", "blobsplat_pyramid",
+                      "blobsplat_scores_ellipse", "blobsplat_composite", "blobsplat_resize_bilinear", "blobsplat_pyramid",
                       "blobsplat_feature_splat", "blobsplat_render"}
 
 

@@ -370,3 +370,48 @@ def test_host_renderer_chunked_copy_matches_single_call():
         torch.cuda.synchronize()
         assert torch.equal(out["scores_pyramid"][s], ref["scores_pyramid"][s])
         assert torch.equal(out["feature_grid"], ref["feature_grid"])
+
+
+def test_ellipse_front_end_matches_script_recipe():
+    """blobsplat_scores_ellipse (N3): all 40 demo ellipses as one batch == the reference's host recipe + renderer
+    (golden fp64 maps), including the two degenerate 1e-5-pixel ellipses (exactly one pixel at 1.0)."""
+    U = _impl()
+    ell = G.ellipses()
+    want = G.arrays()["ellipses/fg64"]
+    batch = torch.tensor([[U.flatten_cv_ellipse(e["ellipse"])] for e in ell], dtype=torch.float32)   # [40, 1, 5]
+    d = U.splat_ellipses(batch.to(DEV), image_size=(512, 512), score_size=64)
+    assert d.shape == (40, 2, 64, 64) and d.dtype == torch.float32
+    got = _np(d)
+    for i, e in enumerate(ell):
+        if e["ellipse"][1] == [1e-05, 1e-05]:
+            assert (got[i, 1] == 1.0).sum() == 1 and (got[i, 1] > 0).sum() == 1 and np.array_equal(got[i, 1] > 0, want[i] > 0)
+        else:
+            close_scaled(got[i, 1], want[i], 1e-5, f"{e['demo']}[{e['idx']}] fg")
+            close_scaled(got[i, 0], 1 - want[i], 1e-5, f"{e['demo']}[{e['idx']}] bg")
+
+
+def test_ellipse_front_end_multi_blob_and_rect():
+    """Several ellipses per image (depth order = index), existence flags, H != W render size, non-square source image."""
+    U = _impl()
+    rng = np.random.default_rng(5)
+    n, m, img_h, img_w, h, w = 3, 6, 384, 640, 40, 72
+    ell = np.stack([rng.uniform(0, img_w, (n, m)), rng.uniform(0, img_h, (n, m)), rng.uniform(20, 300, (n, m)),
+                    rng.uniform(20, 300, (n, m)), rng.uniform(0, 180, (n, m))], -1)
+    sizes = (rng.random((n, m)) > 0.2).astype(np.float32)
+    xs = np.zeros((n, m)); ys = np.zeros((n, m)); covs = np.zeros((n, m, 2, 2))
+    for i in range(n):
+        for j in range(m):
+            e = ((ell[i, j, 0], ell[i, j, 1]), (ell[i, j, 2], ell[i, j, 3]), ell[i, j, 4])
+            mean, cov = blob_oracle.gs_from_ellipse(e)
+            nm, nc = blob_oracle.normalize_gs(mean, cov, img_w, img_h)
+            xs[i, j], ys[i, j], covs[i, j] = nm[0], nm[1], nc
+    raw = blob_oracle.raw_scores(xs, ys, covs, sizes, h, w, np.float64)
+    _, dref = blob_oracle.composite(raw)
+    want = np.moveaxis(dref, -1, 1)
+    got = U.splat_ellipses(torch.from_numpy(ell).float().to(DEV), torch.from_numpy(sizes).to(DEV), image_size=(img_h, img_w),
+                           score_size=(h, w))
+    assert got.shape == (n, m + 1, h, w)
+    close_scaled(_np(got), want, 2e-5, "multi-blob ellipses")     # fp32 ellipse inputs: centre rounding ~3e-5 px
+    fg = U.splat_ellipses(torch.from_numpy(ell).float().to(DEV), torch.from_numpy(sizes).to(DEV), image_size=(img_h, img_w),
+                          score_size=(h, w), only_splatting_fg=True)
+    assert torch.equal(fg, got[:, 1:])
