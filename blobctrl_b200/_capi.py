@@ -48,6 +48,7 @@ SIGNATURES = {
     "blobsplat_resize_bilinear": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_pyramid": [_P, ctypes.POINTER(_P), _I, _I, _I, _I, _I, _P],
     "blobsplat_feature_splat": [_P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "blobsplat_conditioning_fill": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_render": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
 }
 

@@ -34,6 +34,8 @@ int feature_splat_tc_dispatch(const void*, int64_t, int64_t, int64_t, const void
                               cudaStream_t);
 int render_tc_dispatch(const float*, const float*, const float*, const float*, const void*, int, int, int, int, int,
                        int, void*, void*, int, cudaStream_t);
+int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, int,
+                               cudaStream_t);
 int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why);
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
@@ -164,6 +166,24 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
     return feature_splat_tc_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
                                      (cudaStream_t)stream);
   return feature_splat_fma_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
+                                    (cudaStream_t)stream);
+}
+
+int blobsplat_conditioning_fill(const void* scores, const void* features, void* out, int B, int K, int C, int h, int w,
+                                int c_total, int c_off, int halves, int write_scores, int dtype, int device,
+                                void* stream) {
+  BS_CHECK_ARG(B >= 0 && K >= 1 && C >= 0 && h >= 1 && w >= 4 && (w % 4) == 0, "bad shape B=%d K=%d C=%d h=%d w=%d (w %% 4 == 0)", B, K, C, h, w);
+  BS_CHECK_ARG(halves == 1 || halves == 2, "halves must be 1 or 2 (got %d)", halves);
+  const int planes = (write_scores ? K : 0) + C;
+  BS_CHECK_ARG(c_off >= 0 && c_off + planes <= c_total, "channels [%d, %d) outside the buffer's %d", c_off, c_off + planes, c_total);
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  if (B == 0 || planes == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(scores && out && (C == 0 || features), "NULL pointer");
+  BS_CHECK_ARG(aligned_to(out, 16), "output buffer must be 16-byte aligned");
+  BS_CHECK_ARG(B <= 65535, "batch too large");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return conditioning_fill_dispatch(scores, features, out, B, K, C, h, w, c_total, c_off, halves, write_scores, dtype,
                                     (cudaStream_t)stream);
 }
 

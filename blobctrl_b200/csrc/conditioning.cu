@@ -1,0 +1,78 @@
+// N2: fused construct_blobnet_input.
+//
+// Replaces, for the loop-invariant part of BlobNet's input, the per-step
+//   right = cat([latent_model_input, gs_scores, gs_feats], 1); left = cat([image_latents, gs_scores, gs_feats], 1);
+//   blobnet_model_input = cat([left, right], -1)           (blobctrl/pipelines/pipeline_blobnet.py:724-739, called
+//   twice per denoising step at :1043-1049 and :1071-1076) and the stage-3 splat that produced gs_feats (:984).
+// The score plane and the C feature planes (sum_k s_k * f[k,c]) are written ONCE, straight into both width halves of
+// a persistent [B, c_total, h, 2w] buffer at a channel offset; per step only the 4 latent channels are refreshed.
+// Pure streaming stores (K is 1 in the pipeline): one thread = 4 adjacent pixels of one output channel, 128-bit
+// (64-bit for 16-bit dtypes) stores to the left and the right half.
+#include "common.cuh"
+
+namespace blobsplat {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conditioning_fill_kernel(const T* __restrict__ scores, const T* __restrict__ feats, T* __restrict__ out, int K, int C,
+                         int h, int w, int c_total, int c_off, int halves, bool write_scores) {
+  // out[b, c_off + j, y, x + half*w]:  j < K_s (score planes, when write_scores) then C feature planes
+  const int b = blockIdx.z;
+  const int planes = (write_scores ? K : 0) + C;
+  const int P = h * w, w4 = w >> 2;
+  const int items_per_plane = h * w4;
+  const long long total = (long long)planes * items_per_plane;
+  const int Wt = w * halves;
+  const T* sb = scores + (size_t)b * K * P;
+  const T* fb = feats ? feats + (size_t)b * K * C : nullptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int plane = (int)(i / items_per_plane);
+    const int r = (int)(i - (long long)plane * items_per_plane);
+    const int y = r / w4, x = (r - y * w4) << 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (write_scores && plane < K) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (float)Cvt<T>::to(sb[(size_t)plane * P + y * w + x + j]);
+    } else {
+      const int c = plane - (write_scores ? K : 0);
+      for (int k = 0; k < K; ++k) {
+        const float f = (float)Cvt<T>::to(fb[(size_t)k * C + c]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaf((float)Cvt<T>::to(sb[(size_t)k * P + y * w + x + j]), f, v[j]);
+      }
+    }
+    T* o = out + (((size_t)b * c_total + c_off + plane) * h + y) * Wt + x;
+    for (int hf = 0; hf < halves; ++hf) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(o + hf * w) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        T t[4] = {Cvt<T>::from(v[0]), Cvt<T>::from(v[1]), Cvt<T>::from(v[2]), Cvt<T>::from(v[3])};
+        *reinterpret_cast<uint2*>(o + hf * w) = *reinterpret_cast<const uint2*>(t);
+      }
+    }
+  }
+}
+
+template <typename T>
+static int launch_fill(const void* scores, const void* feats, void* out, int B, int K, int C, int h, int w, int c_total,
+                       int c_off, int halves, bool write_scores, cudaStream_t st) {
+  const long long total = (long long)((write_scores ? K : 0) + C) * h * (w >> 2);
+  const unsigned bx = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+  dim3 grid(bx, 1, (unsigned)B);
+  conditioning_fill_kernel<T><<<grid, 256, 0, st>>>((const T*)scores, (const T*)feats, (T*)out, K, C, h, w, c_total, c_off,
+                                                   halves, write_scores);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conditioning_fill_dispatch(const void* scores, const void* feats, void* out, int B, int K, int C, int h, int w,
+                               int c_total, int c_off, int halves, int write_scores, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case BLOBSPLAT_F32: return launch_fill<float>(scores, feats, out, B, K, C, h, w, c_total, c_off, halves, write_scores, st);
+    case BLOBSPLAT_BF16: return launch_fill<__nv_bfloat16>(scores, feats, out, B, K, C, h, w, c_total, c_off, halves, write_scores, st);
+    case BLOBSPLAT_F16: return launch_fill<__half>(scores, feats, out, B, K, C, h, w, c_total, c_off, halves, write_scores, st);
+  }
+  BS_UNSUPPORTED("conditioning fill supports float32/bfloat16/float16 (got %d)", dtype);
+}
+
+}  // namespace blobsplat

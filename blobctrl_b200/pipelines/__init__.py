@@ -1,5 +1,5 @@
-from .conditioning import (BlobConditioning, BlobConditioningMixin, construct_blobnet_input,
+from .conditioning import (BlobConditioning, BlobConditioningMixin, BlobNetInputBuffers, construct_blobnet_input,
                            prepare_blob_conditioning, splat_features_from_scores)
 
-__all__ = ["BlobConditioning", "BlobConditioningMixin", "construct_blobnet_input", "prepare_blob_conditioning",
+__all__ = ["BlobConditioning", "BlobConditioningMixin", "BlobNetInputBuffers", "construct_blobnet_input", "prepare_blob_conditioning",
            "splat_features_from_scores"]

@@ -161,6 +161,20 @@ BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, 
                             int dtype, int engine, int device, void* stream);
 
 /*
+ * (3b) conditioning fill — fused construct_blobnet_input for the loop-invariant channels.
+ *      Replaces the stage-3 splat at pipelines/pipeline_blobnet.py:984 plus the per-step torch.cat of
+ *      construct_blobnet_input (:724-739, called at :1043-1049 and :1071-1076) for everything except the 4 latent
+ *      channels: writes, into a persistent buffer out [B, c_total, h, halves*w] (halves = 2: left | right),
+ *          planes c_off .. c_off+K-1      = scores[b, k]                     (when write_scores != 0)
+ *          planes ..   .. +C-1            = sum_k scores[b, k] * features[b, k, c]
+ *      identically in every width half.  scores [B, K, h, w], features [B, K, C] (NULL when C == 0), same dtype
+ *      (F32/BF16/F16) as out; w % 4 == 0; out 16-byte aligned.
+ */
+BLOBSPLAT_API int blobsplat_conditioning_fill(const void* scores, const void* features, void* out, int B, int K, int C,
+                                int h, int w, int c_total, int c_off, int halves, int write_scores, int dtype,
+                                int device, void* stream);
+
+/*
  * (4) fused render — stages 1+2+3 in ONE launch: blob parameters + features -> composed score maps
  *     and the feature grid at the same resolution, with the per-pixel weights never leaving the SM
  *     (tcgen05 MMA with the weights as the TMEM A operand).  Replaces the whole of splat_features

@@ -415,3 +415,28 @@ def test_ellipse_front_end_multi_blob_and_rect():
     fg = U.splat_ellipses(torch.from_numpy(ell).float().to(DEV), torch.from_numpy(sizes).to(DEV), image_size=(img_h, img_w),
                           score_size=(h, w), only_splatting_fg=True)
     assert torch.equal(fg, got[:, 1:])
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.bfloat16])
+def test_fused_construct_blobnet_input_bit_exact(dtype):
+    """N2: persistent canvases filled by blobsplat_conditioning_fill == the reference's per-step torch.cat layout
+    (pipeline_blobnet.py:724-739) with fg_gs_feats from the stage-3 splat (:984), bit for bit."""
+    from blobctrl_b200.pipelines import BlobNetInputBuffers, construct_blobnet_input, prepare_blob_conditioning
+    U = _impl()
+    b2, h, w, c = 4, 64, 64, 1024
+    e = G.ellipses()[12]["ellipse"]
+    gs = U.splat_ellipses([[U.flatten_cv_ellipse(e)]], image_size=(512, 512), score_size=64)          # [1,2,64,64]
+    g = torch.Generator().manual_seed(7)
+    dino = torch.randn(1, 1, c, generator=g).to(DEV)
+    cond = prepare_blob_conditioning(gs, dino, batch=b2, dtype=dtype, device=DEV)
+    fg_lat = torch.randn(b2, 4, h, w, generator=g).to(DEV).to(dtype)
+    bg_lat = torch.randn(b2, 4, h, w, generator=g).to(DEV).to(dtype)
+    bufs = BlobNetInputBuffers(b2, h, w, c, dtype, DEV)
+    bufs.fill_static(cond.fg_gs_scores, cond.bg_gs_scores, dino.repeat(b2, 1, 1), fg_lat, bg_lat)
+    for step in range(2):
+        lat = torch.randn(b2, 4, h, w, generator=g).to(DEV).to(dtype)
+        x, xb = bufs.update(lat)
+        want = construct_blobnet_input(lat, cond.fg_gs_scores, fg_lat, cond.fg_gs_feats)
+        want_bg = construct_blobnet_input(lat, cond.bg_gs_scores, bg_lat, background=True)
+        assert x.shape == (b2, 4 + 1 + c, h, 2 * w) and xb.shape == (b2, 5, h, 2 * w)
+        assert torch.equal(x, want) and torch.equal(xb, want_bg)
