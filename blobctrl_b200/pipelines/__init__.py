@@ -3,3 +3,6 @@ from .conditioning import (BlobConditioning, BlobConditioningMixin, BlobNetInput
 
 __all__ = ["BlobConditioning", "BlobConditioningMixin", "BlobNetInputBuffers", "construct_blobnet_input", "prepare_blob_conditioning",
            "splat_features_from_scores"]
+from .conv_in_hoist import HoistedConvIn  # noqa: E402
+
+__all__.append("HoistedConvIn")

@@ -119,3 +119,32 @@ def test_product_never_imports_the_oracle():
     import blobctrl_b200  # noqa: F401
     assert not any(m == "oracle" or m.startswith("oracle.") for m in sys.modules
                    if "blobctrl_b200" in (getattr(sys.modules[m], "__file__", "") or ""))
+
+
+def test_hoisted_conv_in_equals_full_conv_cpu():
+    """N1: conv_in over the 4+1+C canvas == per-step 4-channel conv + precomputed static part (pure algebra; CPU)."""
+    from blobctrl_b200.pipelines import HoistedConvIn, construct_blobnet_input
+    g = torch.Generator().manual_seed(0)
+    b2, h, w, c, o, k = 2, 12, 12, 20, 8, 1
+    weight = torch.randn(o, 4 + 1 + c, 3, 3, generator=g) * 0.1
+    bias = torch.randn(o, generator=g)
+    score = torch.rand(b2, 1, h, w, generator=g)
+    f = torch.randn(b2, k, c, generator=g)
+    feats = torch.einsum("nkhw,nkc->nchw", score, f)
+    img_lat = torch.randn(b2, 4, h, w, generator=g)
+    hoist = HoistedConvIn(weight, bias)
+    hoist.prepare(score, score, f)
+    for _ in range(2):
+        lat = torch.randn(b2, 4, h, w, generator=g)
+        full = torch.nn.functional.conv2d(construct_blobnet_input(lat, score, img_lat, feats), weight, bias, padding=1)
+        got = hoist(torch.cat([img_lat, lat], dim=-1))
+        assert got.shape == full.shape == (b2, o, h, 2 * w)
+        assert (got - full).abs().max() <= 1e-4 * full.abs().max()
+    # rank-K conditioning (several blobs): same identity
+    k = 3
+    sk = torch.rand(b2, k, h, w, generator=g); fk = torch.randn(b2, k, c, generator=g)
+    feats = torch.einsum("nkhw,nkc->nchw", sk, fk)
+    hoist.prepare(score, sk, fk)
+    lat = torch.randn(b2, 4, h, w, generator=g)
+    full = torch.nn.functional.conv2d(construct_blobnet_input(lat, score, img_lat, feats), weight, bias, padding=1)
+    assert (hoist(torch.cat([img_lat, lat], dim=-1)) - full).abs().max() <= 1e-4 * full.abs().max()
