@@ -1,0 +1,91 @@
+"""CUDA-graph renderers for the latency-bound uses of the path (BASELINE configs 1-2).
+
+The reference's UI re-renders the blob preview on every mouse event (scripts/blobctrl_app.py:637-650, called from
+:908, :1103, :1151, :1217): one image, one blob, 512x512, and the CLI renders one 64x64 score map per edit
+(scripts/blobctrl_inference.py:112-117).  At those sizes the kernels take a few microseconds and the cost is host
+launch overhead, so the whole render (stages 1+2, and stage 3 with the palette or the features) is captured once in a
+CUDA graph over static buffers; a call copies the ~28 bytes per blob of parameters into place and replays it.
+The C ABI allocates nothing and never synchronises, which is what makes the capture legal.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from .utils.utils import BLOB_VIS_COLORS
+
+
+class GraphedBlobRenderer:
+    """Fixed-shape renderer: N images x M blobs at (H, W); optional stage 3 with ``features`` [N, M+1, C] given per
+    call, or with a fixed colour table (``viz_colors``: the UI preview).  float32 parameters and maps."""
+
+    def __init__(self, n: int, m: int, size: Tuple[int, int], channels: Optional[int] = None,
+                 viz_colors: Optional[torch.Tensor] = None, device="cuda"):
+        self.n, self.m, (self.h, self.w) = n, m, size
+        dev = torch.device(device)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # one flat parameter block (xs | ys | covs | sizes) so a call is ONE host->device copy + one graph replay
+        nm = n * m
+        self.params = torch.zeros(7 * nm, **f32)
+        self.xs = self.params[:nm].view(n, m); self.ys = self.params[nm:2 * nm].view(n, m)
+        self.covs = self.params[2 * nm:6 * nm].view(n, m, 2, 2); self.sizes = self.params[6 * nm:].view(n, m)
+        self.host = torch.zeros(7 * nm, dtype=torch.float32).pin_memory()
+        self._h = self.host.numpy()
+        self._h[2 * nm:6 * nm] = [1, 0, 0, 1] * nm; self._h[6 * nm:] = 1
+        self.params.copy_(self.host)
+        self.feats = None
+        if viz_colors is not None:
+            self.feats = viz_colors[: m + 1].to(**f32)[None].repeat(n, 1, 1).contiguous()     # utils.py:251-253
+        elif channels:
+            self.feats = torch.zeros((n, m + 1, channels), **f32)
+        self.takes_features = viz_colors is None and channels is not None
+        self.stream = torch.cuda.Stream(device=dev)
+        self._run()                                      # warm-up outside capture (loads the kernels)
+        torch.cuda.current_stream(dev).wait_stream(self.stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._run()
+
+    def _run(self):
+        with torch.cuda.stream(self.stream):
+            c = self.feats.shape[-1] if self.feats is not None else 0
+            self.grid = None
+            if self.feats is not None and c % 32 == 0 and c >= 64:
+                try:
+                    self.scores, self.grid = ops.render_fused(self.xs, self.ys, self.covs, self.sizes, self.feats, self.h, self.w)
+                    return
+                except Exception:
+                    pass
+            self.scores, _ = ops.render_scores(self.xs, self.ys, self.covs, self.sizes, self.h, self.w)
+            if self.feats is not None:
+                self.grid = ops.feature_splat(self.scores, self.feats)
+
+    @torch.no_grad()
+    def __call__(self, xs, ys, covs, sizes=None, features=None):
+        """Parameters: host arrays / tensors of any float dtype (the reference's callers build them with numpy on the
+        host, blobctrl_inference.py:101-109); device tensors are accepted but cost a sync.  Returns (composed [N,M+1,H,W], grid | None) —
+        views of the renderer's static output buffers (valid until the next call)."""
+        import numpy as np
+        nm = self.n * self.m
+        to_np = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
+        self._h[:nm] = to_np(xs).reshape(-1); self._h[nm:2 * nm] = to_np(ys).reshape(-1)
+        self._h[2 * nm:6 * nm] = to_np(covs).reshape(-1)
+        if sizes is not None:
+            self._h[6 * nm:] = to_np(sizes).reshape(-1)
+        cur = torch.cuda.current_stream(self.params.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.params.copy_(self.host, non_blocking=True)
+            if features is not None and self.takes_features:
+                self.feats.copy_(features, non_blocking=True)
+            self.graph.replay()
+        cur.wait_stream(self.stream)
+        return self.scores, self.grid
+
+
+def preview_renderer(viz_size=(512, 512), device="cuda") -> GraphedBlobRenderer:
+    """The UI preview of scripts/blobctrl_app.py:637-646 (one image, one blob, BLOB_VIS_COLORS) as a graph:
+    ``scores, img = r(xs, ys, covs)`` -> img [1, 3, H, W] in [0, 1]."""
+    return GraphedBlobRenderer(1, 1, viz_size, viz_colors=BLOB_VIS_COLORS, device=device)

@@ -440,3 +440,26 @@ def test_fused_construct_blobnet_input_bit_exact(dtype):
         want_bg = construct_blobnet_input(lat, cond.bg_gs_scores, bg_lat, background=True)
         assert x.shape == (b2, 4 + 1 + c, h, 2 * w) and xb.shape == (b2, 5, h, 2 * w)
         assert torch.equal(x, want) and torch.equal(xb, want_bg)
+
+
+def test_graphed_renderers_match_eager():
+    """blobctrl_b200.preview: CUDA-graph replay == the eager API (UI preview path and a cfg2-shaped render)."""
+    from blobctrl_b200.preview import GraphedBlobRenderer, preview_renderer
+    U = _impl()
+    r = preview_renderer((128, 128), DEV)
+    for idx in (1, 12, 30):
+        blob = blob_oracle.blob_from_ellipse(G.ellipses()[idx]["ellipse"], 512, 512)
+        b32 = {k: _cuda(v).float() for k, v in blob.items()}
+        scores, img = r(blob["xs"], blob["ys"], blob["covs"])          # host float64 numpy in, like the app
+        want = U.splat_features(**b32, interp_size=64, viz_size=(128, 128), is_viz=True, score_size=64,
+                                viz_score_fn=U.viz_score_fn, viz_colors=U.BLOB_VIS_COLORS, only_vis=True)["feature_img"]
+        torch.cuda.synchronize()
+        assert img.shape == (1, 3, 128, 128) and (img - want).abs().max().item() <= 2e-6
+    syn = blob_oracle.synthetic_blobs(1, 16, seed=3, c=320)
+    g = GraphedBlobRenderer(1, 16, (64, 64), channels=320, device=DEV)
+    for seed in (3, 4):
+        syn = blob_oracle.synthetic_blobs(1, 16, seed=seed, c=320)
+        sc, grid = g(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], _cuda(syn["features"]))
+        ref = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=64, interp_size=64, ret_layout=False)
+        torch.cuda.synchronize()
+        assert torch.equal(sc, ref["scores_pyramid"][64]) and torch.equal(grid, ref["feature_grid"])
