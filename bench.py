@@ -385,6 +385,11 @@ def variants(B, ops, dev, peak):
     out["cfg1_viz_512_latency_us"] = 1e3 * timed(lambda: B.splat_features(
         **b1, interp_size=64, viz_size=(512, 512), is_viz=True, score_size=64, viz_score_fn=B.viz_score_fn,
         viz_colors=B.BLOB_VIS_COLORS, only_vis=True), reps=50)
+    # same preview as a CUDA graph over static buffers (host parameters in, one copy + one replay per call)
+    from blobctrl_b200.preview import preview_renderer
+    pr = preview_renderer((512, 512), dev)
+    hx, hy, hc = hb["xs"].numpy(), hb["ys"].numpy(), hb["covs"].numpy()
+    out["cfg1_viz_512_graph_latency_us"] = 1e3 * timed(lambda: pr(hx, hy, hc), reps=50)
     return out
 
 
