@@ -80,10 +80,10 @@ int blobsplat_scores(const void* xs, const void* ys, const void* covs, const flo
   BS_CHECK_ARG(select >= BLOBSPLAT_SELECT_ALL && select <= BLOBSPLAT_SELECT_BG, "bad select %d", select);
   BS_CHECK_ARG(composite_mode >= BLOBSPLAT_COMPOSITE_AUTO && composite_mode <= BLOBSPLAT_COMPOSITE_WARP_SCAN,
                "bad composite_mode %d", composite_mode);
+  if (N == 0) return BLOBSPLAT_OK;   // empty batch: nothing to render (buffers of an empty tensor are NULL)
   BS_CHECK_ARG(composed || raw, "both outputs are NULL");
   BS_CHECK_ARG(!composed || valid_dtype(composed_dtype), "bad composed dtype %d", composed_dtype);
   BS_CHECK_ARG(!raw || valid_dtype(raw_dtype), "bad raw dtype %d", raw_dtype);
-  if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
   DeviceGuard g(device);
   if (g.status) return g.status;
@@ -98,10 +98,10 @@ int blobsplat_scores_ellipse(const float* ellipses, const float* sizes, float im
   BS_CHECK_ARG(M <= kMaxBlobs && N <= 65535 && (long long)H * W < (1ll << 31), "shape too large");
   BS_CHECK_ARG(img_w > 0.f && img_h > 0.f, "bad image size %g x %g", (double)img_w, (double)img_h);
   BS_CHECK_ARG(select >= BLOBSPLAT_SELECT_ALL && select <= BLOBSPLAT_SELECT_BG, "bad select %d", select);
+  if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(composed || raw, "both outputs are NULL");
   BS_CHECK_ARG(!composed || valid_dtype(composed_dtype), "bad composed dtype %d", composed_dtype);
   BS_CHECK_ARG(!raw || valid_dtype(raw_dtype), "bad raw dtype %d", raw_dtype);
-  if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(M == 0 || (ellipses && sizes), "NULL ellipse parameter pointer");
   DeviceGuard g(device);
   if (g.status) return g.status;

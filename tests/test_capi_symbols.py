@@ -58,6 +58,7 @@ def test_caps_and_argument_validation_without_a_gpu():
     assert "bad shape" in _capi.last_error()
     assert L.blobsplat_scores(None, None, None, None, 0, 1, 1, 8, 8, 0, None, 0, None, 0, 0, -1, None) == -1
     assert "NULL" in _capi.last_error()
+    assert L.blobsplat_scores(None, None, None, None, 0, 0, 1, 8, 8, 0, None, 0, None, 0, 0, -1, None) == 0   # N == 0
     assert L.blobsplat_pyramid(None, None, 3, 1, 20, 0, -1, None) == -1
     assert "divisible" in _capi.last_error()
     with pytest.raises(ValueError):

@@ -463,3 +463,85 @@ def test_graphed_renderers_match_eager():
         ref = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=64, interp_size=64, ret_layout=False)
         torch.cuda.synchronize()
         assert torch.equal(sc, ref["scores_pyramid"][64]) and torch.equal(grid, ref["feature_grid"])
+
+
+def test_empty_and_degenerate_shapes():
+    """No blobs (M = 0): the background owns every pixel; no images (N = 0): empty outputs, no launch."""
+    U = _impl()
+    xs = torch.zeros(2, 0, device=DEV); covs = torch.zeros(2, 0, 2, 2, device=DEV); sizes = torch.zeros(2, 0, device=DEV)
+    d = U.splat_features(xs, xs, covs, sizes, score_size=8, return_d_score=True)
+    assert d.shape == (2, 1, 8, 8) and torch.equal(d, torch.ones_like(d))
+    e = U.splat_features(torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, device=DEV), torch.zeros(0, 3, 2, 2, device=DEV),
+                         torch.zeros(0, 3, device=DEV), score_size=8, return_d_score=True)
+    assert e.shape == (0, 4, 8, 8)
+    g = U.splat_features_from_scores(torch.zeros(0, 4, 8, 8, device=DEV), torch.zeros(0, 4, 5, device=DEV), 8, channels_last=False)
+    assert g.shape == (0, 5, 8, 8)
+
+
+def test_randomised_shapes_vs_oracle():
+    """Seeded sweep over ragged shapes (any N, M, H != W, C) through the general [N,M] renderer and both stage-3 engines."""
+    from blobctrl_b200 import ops
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        n, m = int(rng.integers(1, 4)), int(rng.integers(1, 41))
+        h, w = int(rng.integers(1, 41)), int(rng.integers(1, 41))
+        c = int(rng.choice([1, 3, 7, 32, 64, 96]))
+        syn = blob_oracle.synthetic_blobs(n, m, seed=100 + it, thin=bool(it % 5 == 0), c=c)
+        raw = blob_oracle.raw_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], h, w, np.float64)
+        _, dref = blob_oracle.composite(raw)
+        want_d = np.moveaxis(dref, -1, 1)
+        b = _blob(syn)
+        d, r = ops.render_scores(b["xs"], b["ys"], b["covs"], b["sizes"], h, w, want_raw=True)
+        close_scaled(_np(d), want_d, 2e-5 if it % 5 == 0 else 1e-5, f"case {it} composed {n}x{m}x{h}x{w}")
+        close_scaled(_np(r)[:, 1:], np.moveaxis(raw, -1, 1), 2e-5 if it % 5 == 0 else 1e-5, f"case {it} raw")
+        want_g = blob_oracle.splat_features_from_scores(want_d, syn["features"].astype(np.float64), None, channels_last=False)
+        for eng in ("fma", "auto"):
+            g = ops.feature_splat(d, _cuda(syn["features"]), engine=eng)
+            close_scaled(_np(g), want_g, 2e-5, f"case {it} grid C={c} {eng}")
+
+
+def test_input_forms_noncontiguous_half_params_and_large_image():
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, 5, seed=31)
+    want = blob_oracle.render_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], 16, 16, np.float64)
+    covs_nc = _cuda(syn["covs"]).permute(0, 1, 3, 2).contiguous().permute(0, 1, 3, 2)       # non-contiguous view
+    assert not covs_nc.is_contiguous()
+    d = U.splat_features(_cuda(syn["xs"]), _cuda(syn["ys"]), covs_nc, _cuda(syn["sizes"]), score_size=16, return_d_score=True)
+    close_scaled(_np(d), want, 1e-5, "non-contiguous covs")
+    # bfloat16 parameters: the reference cannot run them at all ("lu_cpu" not implemented); here they are upcast
+    h = {k: (_cuda(v).to(torch.bfloat16) if k != "sizes" else _cuda(v)) for k, v in syn.items()}
+    dh = U.splat_features(**h, score_size=16, return_d_score=True)
+    assert dh.dtype == torch.bfloat16
+    want_h = blob_oracle.render_scores(_np(h["xs"]), _np(h["ys"]), _np(h["covs"]), syn["sizes"], 16, 16, np.float64)
+    close_scaled(_np(dh), want_h, 1e-2, "bf16 parameters")
+    # one blob on a 1024 x 1024 canvas, float32 and float64 (tuple-size path)
+    one = blob_oracle.blob_from_ellipse(((500.0, 300.0), (400.0, 150.0), 33.0), 1024, 1024)
+    w64 = blob_oracle.splat_features(**one, score_size=(1024, 1024), return_d_score=True)
+    g64 = U.splat_features(**{k: _cuda(v) for k, v in one.items()}, score_size=(1024, 1024), return_d_score=True)
+    assert g64.dtype == torch.float64
+    close_scaled(_np(g64), w64, 1e-9, "1024^2 fp64")
+    g32 = U.splat_features(**{k: _cuda(v).float() for k, v in one.items()}, score_size=(1024, 1024), return_d_score=True)
+    close_scaled(_np(g32), w64, 1e-5, "1024^2 fp32")
+
+
+def test_full_size_config3_properties():
+    """BASELINE config 3 at full batch (N=64, 32 blobs, levels 64/32/16/8, C=320/640/1280/1280, bf16): shapes, dtype,
+    partition of unity at every level, and agreement of a 2-image slice with the float64 oracle."""
+    U = _impl()
+    n, m = 64, 32
+    syn = blob_oracle.synthetic_blobs(n, m, seed=0)
+    chans = {64: 320, 32: 640, 16: 1280, 8: 1280}
+    g = torch.Generator().manual_seed(1)
+    feats = {s: torch.randn(n, m + 1, c, generator=g).to(DEV).to(torch.bfloat16) for s, c in chans.items()}
+    out = U.splat_features_multiscale(**_blob(syn), score_size=64, level_features=feats, out_dtype=torch.bfloat16)
+    for s, c in chans.items():
+        sc, gr = out["scores_pyramid"][s], out["feature_grids"][s]
+        assert sc.shape == (n, m + 1, s, s) and gr.shape == (n, c, s, s) and gr.dtype == torch.bfloat16
+        assert (sc.float().sum(1) - 1).abs().max().item() <= 2e-2
+    sl = slice(30, 32)
+    d = blob_oracle.render_scores(syn["xs"][sl], syn["ys"][sl], syn["covs"][sl], syn["sizes"][sl], 64, 64, np.float64)
+    pyr = blob_oracle.pyramid_resize(d, 8)
+    for s in chans:
+        close_scaled(_np(out["scores_pyramid"][s][sl]), pyr[s], 1e-2, f"cfg3 scores@{s}")
+        want = blob_oracle.splat_features_from_scores(pyr[s], _np(feats[s][sl]).astype(np.float64), s, channels_last=False)
+        close_scaled(_np(out["feature_grids"][s][sl]), want, 1e-2, f"cfg3 grid@{s}")
