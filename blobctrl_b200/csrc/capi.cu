@@ -36,6 +36,7 @@ int render_tc_dispatch(const float*, const float*, const float*, const float*, c
                        int, void*, void*, int, cudaStream_t);
 int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, int,
                                cudaStream_t);
+int residual_inject_dispatch(void*, const void*, const float*, float, int, int, int, int, int, int, int, cudaStream_t);
 int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why);
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
@@ -185,6 +186,18 @@ int blobsplat_conditioning_fill(const void* scores, const void* features, void* 
   if (g.status) return g.status;
   return conditioning_fill_dispatch(scores, features, out, B, K, C, h, w, c_total, c_off, halves, write_scores, dtype,
                                     (cudaStream_t)stream);
+}
+
+int blobsplat_residual_inject(void* hidden, const void* residual, const float* scale_per_sample, float scale, int B, int C,
+                              int H, int Wh, int Wr, int cols, int dtype, int device, void* stream) {
+  BS_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && Wh >= 1 && Wr >= 1, "bad shape");
+  BS_CHECK_ARG(cols >= 1 && cols <= Wh && cols <= Wr, "cols=%d must fit both widths (%d, %d)", cols, Wh, Wr);
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  if (B == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(hidden && residual, "NULL pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return residual_inject_dispatch(hidden, residual, scale_per_sample, scale, B, C, H, Wh, Wr, cols, dtype, (cudaStream_t)stream);
 }
 
 int blobsplat_render(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,

@@ -76,3 +76,59 @@ int conditioning_fill_dispatch(const void* scores, const void* feats, void* out,
 }
 
 }  // namespace blobsplat
+
+// N4: fused BlobNet residual injection.
+// Replaces, per residual, the three elementwise passes of the reference loop:
+//   residual * conditioning_scale                      (blobctrl/models/blobnet.py:936-938)
+//   residual[..., -h:]                                 (blobctrl/pipelines/pipeline_blobnet.py:1085-1087, a slice copy)
+//   sample[..., -h:] = sample[..., -h:] + residual     (diffusers/.../unet_2d_condition.py:1215-1219 and the block
+//                                                       variants in unet_2d_blocks.py:1303-1319, 2598-2615)
+// with one in-place pass over the right-hand `cols` columns: hidden[b,c,y,Wh-cols+x] += scale_b * residual[b,c,y,Wr-cols+x].
+// Rounding follows the reference op by op (scaled residual rounded to the tensor dtype, then the sum rounded).
+namespace blobsplat {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+residual_inject_kernel(T* __restrict__ hidden, const T* __restrict__ residual, const float* __restrict__ scale_b, float scale,
+                       long long rows_per_sample, long long rows, int Wh, int Wr, int cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cols;
+    const int x = (int)(i - row * cols);
+    const float s = scale_b ? scale_b[row / rows_per_sample] : scale;
+    const T r = residual[row * Wr + (Wr - cols) + x];
+    T* h = hidden + row * Wh + (Wh - cols) + x;
+    if constexpr (sizeof(T) == 8) {
+      *h = __dadd_rn(*h, __dmul_rn(r, (double)s));
+    } else {
+      // explicit _rn intrinsics: no FMA contraction, the reference rounds the product before the sum
+      const T scaled = Cvt<T>::from(__fmul_rn((float)Cvt<T>::to(r), s));
+      *h = Cvt<T>::from(__fadd_rn((float)Cvt<T>::to(*h), (float)Cvt<T>::to(scaled)));
+    }
+  }
+}
+
+template <typename T>
+static int launch_inject(void* hidden, const void* residual, const float* scale_b, float scale, int B, int C, int H, int Wh,
+                         int Wr, int cols, cudaStream_t st) {
+  const long long rows = (long long)B * C * H;
+  const long long total = rows * cols;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  residual_inject_kernel<T><<<blocks, 256, 0, st>>>((T*)hidden, (const T*)residual, scale_b, scale, (long long)C * H, rows, Wh,
+                                                   Wr, cols);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int residual_inject_dispatch(void* hidden, const void* residual, const float* scale_b, float scale, int B, int C, int H, int Wh,
+                             int Wr, int cols, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case BLOBSPLAT_F32: return launch_inject<float>(hidden, residual, scale_b, scale, B, C, H, Wh, Wr, cols, st);
+    case BLOBSPLAT_F64: return launch_inject<double>(hidden, residual, scale_b, scale, B, C, H, Wh, Wr, cols, st);
+    case BLOBSPLAT_BF16: return launch_inject<__nv_bfloat16>(hidden, residual, scale_b, scale, B, C, H, Wh, Wr, cols, st);
+    case BLOBSPLAT_F16: return launch_inject<__half>(hidden, residual, scale_b, scale, B, C, H, Wh, Wr, cols, st);
+  }
+  BS_UNSUPPORTED("unknown dtype %d", dtype);
+}
+
+}  // namespace blobsplat

@@ -110,6 +110,28 @@ class BlobNetInputBuffers:
         return self.blobnet_input, self.unet_bg_input
 
 
+def inject_residual(hidden: torch.Tensor, residual: torch.Tensor, conditioning_scale=1.0) -> torch.Tensor:
+    """N4: ``hidden[..., -h:] += conditioning_scale * residual[..., -h:]`` in place, one pass (h = hidden.shape[-2]; on a
+    square map the whole width).  Fuses models/blobnet.py:936-938, pipeline_blobnet.py:1085-1087 and
+    unet_2d_condition.py:1215-1219.  ``conditioning_scale``: float or a per-sample tensor [B]."""
+    from .. import _capi as C
+    C.require_cuda(hidden, "hidden")
+    if not (hidden.is_contiguous() and residual.is_contiguous()) or hidden.dtype != residual.dtype:
+        raise RuntimeError("inject_residual needs contiguous tensors of one dtype")
+    b, c, h, wh = hidden.shape
+    wr = residual.shape[-1]
+    cols = min(h, wh) if wh != h else wh
+    sb = None
+    sc = 1.0
+    if torch.is_tensor(conditioning_scale):
+        sb = conditioning_scale.to(device=hidden.device, dtype=hidden.dtype).float().reshape(b).contiguous()
+    else:
+        sc = float(conditioning_scale)
+    C.check(C.lib().blobsplat_residual_inject(C.ptr(hidden), C.ptr(residual), C.ptr(sb), sc, b, c, h, wh, wr, cols,
+                                              C.dtype_code(hidden.dtype), C.dev_of(hidden), C.stream_of(hidden)))
+    return hidden
+
+
 class BlobConditioningMixin:
     """Method-compatible replacements for StableDiffusionBlobNetPipeline's two conditioning methods."""
 

@@ -175,6 +175,18 @@ BLOBSPLAT_API int blobsplat_conditioning_fill(const void* scores, const void* fe
                                 int device, void* stream);
 
 /*
+ * (3c) residual injection — fused scale + right-half slice + add.  Replaces, per BlobNet
+ *      residual and denoising step, `residual * conditioning_scale` (models/blobnet.py:936-938), the slice
+ *      `residual[..., -h:]` (pipelines/pipeline_blobnet.py:1085-1087) and `sample[..., -h:] += residual`
+ *      (diffusers/src/diffusers/models/unets/unet_2d_condition.py:1215-1219; unet_2d_blocks.py:1303-1319, 2598-2615):
+ *          hidden[b, c, y, Wh - cols + x] += scale_b * residual[b, c, y, Wr - cols + x],   x < cols   (in place)
+ *      hidden [B, C, H, Wh], residual [B, C, H, Wr] contiguous, same dtype; scale_per_sample: device float[B] or NULL
+ *      (then the scalar `scale` applies).  Rounded op by op like the reference (bit-identical in fp16/bf16/fp32).
+ */
+BLOBSPLAT_API int blobsplat_residual_inject(void* hidden, const void* residual, const float* scale_per_sample, float scale,
+                              int B, int C, int H, int Wh, int Wr, int cols, int dtype, int device, void* stream);
+
+/*
  * (4) fused render — stages 1+2+3 in ONE launch: blob parameters + features -> composed score maps
  *     and the feature grid at the same resolution, with the per-pixel weights never leaving the SM
  *     (tcgen05 MMA with the weights as the TMEM A operand).  Replaces the whole of splat_features

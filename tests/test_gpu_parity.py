@@ -545,3 +545,24 @@ def test_full_size_config3_properties():
         close_scaled(_np(out["scores_pyramid"][s][sl]), pyr[s], 1e-2, f"cfg3 scores@{s}")
         want = blob_oracle.splat_features_from_scores(pyr[s], _np(feats[s][sl]).astype(np.float64), s, channels_last=False)
         close_scaled(_np(out["feature_grids"][s][sl]), want, 1e-2, f"cfg3 grid@{s}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_residual_injection_bit_exact(dtype):
+    """N4: fused scale + right-half slice + add == the reference's three elementwise passes (blobnet.py:936-938,
+    pipeline_blobnet.py:1085-1087, unet_2d_condition.py:1215-1219), bit for bit, for float and per-sample scales."""
+    from blobctrl_b200.pipelines import inject_residual
+    g = torch.Generator().manual_seed(11)
+    b, c, h = 4, 37, 16
+    hidden = torch.randn(b, c, h, 2 * h, generator=g).to(DEV).to(dtype)
+    res = torch.randn(b, c, h, 2 * h, generator=g).to(DEV).to(dtype)
+    for scale in (1.2, torch.tensor([0.5, 1.0, 1.2, 0.0]).to(DEV).to(dtype)):
+        s = scale if not torch.is_tensor(scale) else scale[:, None, None, None]
+        scaled = res * s                                             # blobnet.py:936-938
+        cropped = scaled[..., -scaled.shape[-2]:]                    # pipeline_blobnet.py:1085-1087
+        want = hidden.clone()
+        want[..., -want.shape[-2]:] = want[..., -want.shape[-2]:] + cropped     # unet_2d_condition.py:1218
+        got = inject_residual(hidden.clone(), res, scale)
+        assert torch.equal(got, want)
+    sq = torch.randn(2, 8, h, h, generator=g).to(DEV).to(dtype); rq = torch.randn(2, 8, h, h, generator=g).to(DEV).to(dtype)
+    assert torch.equal(inject_residual(sq.clone(), rq, 0.7), sq + rq * 0.7)    # square map: whole width (:1216)
