@@ -305,7 +305,16 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
 #ifndef BS_SPLIT_NUM
 #define BS_SPLIT_NUM 7
 #endif
-      const int m_split = kHalves == 2 ? (((p.M * BS_SPLIT_NUM) >> 4) & ~3) : 0;   // multiple of 4: whole unrolled groups
+#ifndef BS_SPLIT_ALIGN
+#define BS_SPLIT_ALIGN 8
+#endif
+      // front range = M - m_split blobs: both ranges are whole groups of 8 whenever M is (no serial tail blobs; the
+      // serial tail costs ~2.3x per blob), and the back range stays the smaller one because it also rescales
+      int m_split = 0;
+      if (kHalves == 2) {
+        m_split = ((p.M * BS_SPLIT_NUM) >> 4) & ~(BS_SPLIT_ALIGN - 1);
+        if (BS_SPLIT_ALIGN == 8 && ((p.M - m_split) & 7) != 0 && (p.M & 7) == 0) m_split = (p.M * BS_SPLIT_NUM >> 4) & ~7;
+      }
       const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
       const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
