@@ -43,6 +43,10 @@ namespace blobsplat {
 // compositing one of two blob ranges.  Threads = (4*kHalves compute + 4 epilogue + 1 MMA) warps = 288 / 416.
 constexpr int kTcTileM = 128;
 constexpr int kTcMaxCTile = 320;
+// Plane k (0 = background, m+1 = blob m) lives at operand row / TMEM column / stash column k + kTcKOff: with the
+// offset 3 every group of 8 blobs of a range that ends on a multiple of 8 occupies two 16-byte aligned float4s of the
+// pixel-major stash, so stage 1/2, the rescale pass and the TMEM conversion all use 128-bit shared-memory accesses.
+constexpr int kTcKOff = 3;
 constexpr int kTcMaxBlobs = 127;                 // coefficient table: 127 * 32 B
 constexpr size_t kTcSmemBudget = 227 * 1024 - 256;
 
@@ -194,8 +198,9 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   const int c_half = p.c_tile >> 1;
   const size_t b_bytes = (size_t)(p.Kp / kElemsPer16B) * p.c_tile * 16;   // one B copy
   unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
-  float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [Kp][128] composed weights of one tile
-  float* carry = stash + (size_t)p.Kp * kTcTileM;                         // [128] front-range transmittance per pixel
+  const int srow = p.Kp + 4;                                               // stash row stride (floats): conflict-free LDS/STS.128
+  float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [128 pixels][Kp + 4] composed weights of one tile
+  float* carry = stash + (size_t)srow * kTcTileM;                         // [128] front-range transmittance per pixel
   BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
 
@@ -251,6 +256,9 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
         my_general |= bc.flags & kGeneral;
         coef[i] = bc;
       }
+      if (unit_it == 0) {   // stash columns that are never written (k' < kTcKOff, k' >= K + kTcKOff) stay zero for the whole kernel
+        for (int i = ctid; i < kTcTileM * srow; i += kTcComputeThreads) stash[i] = 0.0f;
+      }
       if (unit_it > 0) mbar_wait(&bars->b_free, (unit_it - 1) & 1);   // MMAs of the previous unit have read B
       {
         // features [K, C] (c contiguous) -> K-major 16-byte k-chunks per channel; 4 items (16 B each) per
@@ -267,8 +275,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             const int ch = c0 + c;
 #pragma unroll
             for (int j = 0; j < kElemsPer16B; ++j) {
-              const int k = kc * kElemsPer16B + j;
-              v[b][j] = (i < items && k < p.K && ch < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch)) : 0.0f;
+              const int k = kc * kElemsPer16B + j - kTcKOff;            // operand row k' = k + kTcKOff
+              v[b][j] = (i < items && k >= 0 && k < p.K && ch < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch)) : 0.0f;
             }
           }
 #pragma unroll
@@ -323,7 +331,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
         const bool live = pix < P;
         const int y = live ? pix / p.W : 0;
         const float xf = (float)(live ? pix - y * p.W : 0), yf = (float)y;
-        float* my = stash + px;
+        float* my = stash + (size_t)px * srow + kTcKOff;          // my[k] = plane k of this pixel
         if constexpr (kFromScores) {
           // stand-alone stage 3: this pixel's K weights come from global memory (plane-contiguous, coalesced
           // across lanes for [N,K,H,W]); the two warps of a quarter split the planes
@@ -336,40 +344,44 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)(k + j) * p.sk)) : 0.0f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) my[(size_t)(k + j) * kTcTileM] = v[j];
+            for (int j = 0; j < 8; ++j) my[k + j] = v[j];
           }
-          for (; k < k_hi; ++k) my[(size_t)k * kTcTileM] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)k * p.sk)) : 0.0f;
-          if (half == 0) {
-            for (int kk = p.K; kk < p.Kp; ++kk) my[(size_t)kk * kTcTileM] = 0.0f;
-          }
+          for (; k < k_hi; ++k) my[k] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)k * p.sk)) : 0.0f;
         } else {
           float T = 1.0f;
           const bool wr = comp != nullptr && live;
           const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
           OT* const comp_px = comp + pix;                 // this pixel in plane 0; plane k is + k*P
           int m = m_hi;
-          if (!any_general) {
-            // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
-            // transmittance T is a serial dependence (one FFMA per blob)
-            for (; m >= m_lo + 8; m -= 8) {
-              float s[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
-              OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float d = s[j] * T;
-                T = fmaf(-s[j], T, T);
-                my[(size_t)(m - j) * kTcTileM] = d;
-                if (wr_now) __stcs(cp - (ptrdiff_t)j * P, Cvt<OT>::from(d));
-              }
-            }
-          }
-          for (; m >= m_lo + 1; --m) {
+          // serial head until the remaining blobs of the range are whole, float4-aligned groups of 8
+          for (; m >= m_lo + 1 && (any_general || (m & 7) != 0 || m < m_lo + 8); --m) {
             const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
             const float d = s * T;
             T = fmaf(-s, T, T);
-            my[(size_t)m * kTcTileM] = d;
+            my[m] = d;
+            if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
+          }
+          // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
+          // transmittance T is a serial dependence (one FFMA per blob).  Planes m-7..m are two aligned float4s.
+          for (; m >= m_lo + 8; m -= 8) {
+            float s[8], d[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
+            OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              d[j] = s[j] * T;
+              T = fmaf(-s[j], T, T);
+              if (wr_now) __stcs(cp - (ptrdiff_t)j * P, Cvt<OT>::from(d[j]));
+            }
+            *reinterpret_cast<float4*>(my + m - 7) = make_float4(d[7], d[6], d[5], d[4]);
+            *reinterpret_cast<float4*>(my + m - 3) = make_float4(d[3], d[2], d[1], d[0]);
+          }
+          for (; m >= m_lo + 1; --m) {               // (only when the range is shorter than 8 after the head)
+            const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
+            const float d = s * T;
+            T = fmaf(-s, T, T);
+            my[m] = d;
             if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
           }
           if constexpr (kHalves == 2) {
@@ -380,19 +392,31 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             float c = 1.0f;
             if constexpr (kHalves == 2) {
               c = carry[px];
-#pragma unroll 4
-              for (int k = m_hi; k >= 1; --k) {
-                const float v = my[(size_t)k * kTcTileM] * c;
-                my[(size_t)k * kTcTileM] = v;
+              int k = m_hi;
+              for (; k >= 1 && ((k & 3) != 0 || k < 4); --k) {       // unaligned top of the range
+                const float v = my[k] * c;
+                my[k] = v;
+                if (wr) __stcs(comp_px + (size_t)k * P, Cvt<OT>::from(v));
+              }
+              for (; k >= 4; k -= 4) {                                // planes k-3..k: one aligned float4
+                float4 v4 = *reinterpret_cast<const float4*>(my + k - 3);
+                v4.x *= c; v4.y *= c; v4.z *= c; v4.w *= c;
+                *reinterpret_cast<float4*>(my + k - 3) = v4;
+                if (wr) {
+                  OT* const cp = comp_px + (size_t)k * P;
+                  __stcs(cp, Cvt<OT>::from(v4.w)); __stcs(cp - (ptrdiff_t)P, Cvt<OT>::from(v4.z));
+                  __stcs(cp - (ptrdiff_t)2 * P, Cvt<OT>::from(v4.y)); __stcs(cp - (ptrdiff_t)3 * P, Cvt<OT>::from(v4.x));
+                }
+              }
+              for (; k >= 1; --k) {
+                const float v = my[k] * c;
+                my[k] = v;
                 if (wr) __stcs(comp_px + (size_t)k * P, Cvt<OT>::from(v));
               }
             }
             const float bg = T * c;                     // background: alpha 1 * total transmittance
             my[0] = bg;
             if (wr) __stcs(comp_px, Cvt<OT>::from(bg));
-          }
-          if (half == 0) {
-            for (int k = p.K; k < p.Kp; ++k) my[(size_t)k * kTcTileM] = 0.0f;
           }
         }
         if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
@@ -403,9 +427,12 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
         if constexpr (kTf32) {
           for (int g = half; g < p.Kp / 8; g += kHalves) {  // the warps of a quarter interleave the k-groups
             uint32_t hi[8], lo[8];
+            const float4 wa = *reinterpret_cast<const float4*>(my - kTcKOff + g * 8);      // operand rows 8g .. 8g+7
+            const float4 wb = *reinterpret_cast<const float4*>(my - kTcKOff + g * 8 + 4);
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float w = live ? my[(size_t)(g * 8 + j) * kTcTileM] : 0.0f;
+              const float w = live ? wv[j] : 0.0f;
               const float h = rna_tf32(w);
               hi[j] = __float_as_uint(h);
               lo[j] = __float_as_uint(rna_tf32(w - h));
@@ -417,10 +444,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           // two k per 32-bit column (low half = even k): 8 columns = 16 consecutive k
           for (int g = half; g < p.Kp / 16; g += kHalves) {
             uint32_t pk[8];
+            const float* row = my - kTcKOff + g * 16;                                       // operand rows 16g .. 16g+15
+            const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(row + 8), q3 = *reinterpret_cast<const float4*>(row + 12);
+            const float wv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float w0 = live ? my[(size_t)(g * 16 + 2 * j) * kTcTileM] : 0.0f;
-              const float w1 = live ? my[(size_t)(g * 16 + 2 * j + 1) * kTcTileM] : 0.0f;
+              const float w0 = live ? wv[2 * j] : 0.0f;
+              const float w1 = live ? wv[2 * j + 1] : 0.0f;
               OT lo16 = Cvt<OT>::from(w0), hi16 = Cvt<OT>::from(w1);
               pk[j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo16)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi16)) << 16);
             }
@@ -541,12 +572,12 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
   TcPlan pl{};
   pl.ok = false;
   const int kstep = tf32 ? 8 : 16;
-  pl.Kp = round_up(K, kstep);
+  pl.Kp = round_up(K + kTcKOff, kstep);
   if (K - 1 > kTcMaxBlobs) { pl.why = "more than 127 blobs: use the FMA engine"; return pl; }
   if (C % 32 != 0) { pl.why = "C must be a multiple of 32 for the tensor-core render"; return pl; }
   const int a_cols = tf32 ? 2 * pl.Kp : pl.Kp / 2;
   const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : 2);                  // B bytes per channel (hi+lo fp32 | 16-bit)
-  const size_t fixed = (size_t)pl.Kp * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
+  const size_t fixed = (size_t)(pl.Kp + 4) * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
   int c_tile = std::min(kTcMaxCTile, C);
   c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);

@@ -8,8 +8,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "cur": "",
-    "split_align4": "-DBS_SPLIT_ALIGN=4",
-    "split8_32_32": "-DBS_SPLIT_NUM=8",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 
