@@ -261,40 +261,48 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       }
       if (unit_it > 0) mbar_wait(&bars->b_free, (unit_it - 1) & 1);   // MMAs of the previous unit have read B
       {
-        // features [K, C] (c contiguous) -> K-major 16-byte k-chunks per channel; 4 items (16 B each) per
-        // thread per round so 4*T global loads are in flight before the first conversion
+        // features [K, C] (c contiguous) -> K-major operand rows: item (kc, c) = the T k-values kc*T .. kc*T+T-1 of
+        // channel c as one 16-byte chunk.  One thread moves a T x VC block: T 128-bit global loads (VC adjacent
+        // channels of one feature row each, coalesced across the warp), transposed in registers into VC items.
         const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
-        const int items = (p.Kp / kElemsPer16B) * p.c_tile;
-        constexpr int kBatch = 4;
-        for (int i0 = ctid; i0 < items; i0 += kTcComputeThreads * kBatch) {
-          float v[kBatch][kElemsPer16B];
+        constexpr int T = kElemsPer16B;
+        constexpr int VC = 16 / sizeof(FT);
+        const int cq = p.c_tile / VC;
+        const int blocks = (p.Kp / T) * cq;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C % VC) == 0;
+        for (int qi = ctid; qi < blocks; qi += kTcComputeThreads) {
+          const int kc = qi / cq, c = (qi - kc * cq) * VC;
+          const int ch = c0 + c;
+          float v[T][VC];
 #pragma unroll
-          for (int b = 0; b < kBatch; ++b) {
-            const int i = i0 + b * kTcComputeThreads;
-            const int kc = i / p.c_tile, c = i - kc * p.c_tile;
-            const int ch = c0 + c;
+          for (int j = 0; j < T; ++j) {
+            const int k = kc * T + j - kTcKOff;                          // operand row k' = k + kTcKOff
+            const bool ok = k >= 0 && k < p.K && ch < p.C;
+            if (ok && vec_ok) {
+              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(f + (size_t)k * p.C + ch));
+              const FT* e = reinterpret_cast<const FT*>(&raw);
 #pragma unroll
-            for (int j = 0; j < kElemsPer16B; ++j) {
-              const int k = kc * kElemsPer16B + j - kTcKOff;            // operand row k' = k + kTcKOff
-              v[b][j] = (i < items && k >= 0 && k < p.K && ch < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch)) : 0.0f;
+              for (int cc = 0; cc < VC; ++cc) v[j][cc] = (float)Cvt<FT>::to(e[cc]);
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < VC; ++cc)
+                v[j][cc] = (ok && ch + cc < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch + cc)) : 0.0f;
             }
           }
+          unsigned char* dst = b_smem + ((size_t)kc * p.c_tile + c) * 16;
 #pragma unroll
-          for (int b = 0; b < kBatch; ++b) {
-            const int i = i0 + b * kTcComputeThreads;
-            if (i >= items) break;
-            unsigned char* dst = b_smem + (size_t)i * 16;
+          for (int cc = 0; cc < VC; ++cc) {
             if constexpr (kTf32) {
               float hi[4], lo[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[b][j]); lo[j] = rna_tf32(v[b][j] - hi[j]); }
-              *reinterpret_cast<float4*>(dst) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(dst + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+              for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j][cc]); lo[j] = rna_tf32(v[j][cc] - hi[j]); }
+              *reinterpret_cast<float4*>(dst + cc * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<float4*>(dst + cc * 16 + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             } else {
               OT h[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[b][j]);
-              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+              for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[j][cc]);
+              *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h);
             }
           }
         }
