@@ -262,8 +262,8 @@ def main():
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": peak,
             "unit": "GB/s", "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the
-            # ncu --set full capture summarised in profiles/render_tc_r1.md (0.0872 GB read + 6.3991 GB written)
-            "traffic": 6486316744 if dom["name"].startswith("render_tc") else None,
+            # ncu --set full capture summarised in profiles/render_tc_r1.md (0.0872 GB read + 6.4000 GB written)
+            "traffic": 6487169744 if dom["name"].startswith("render_tc") else None,
             "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["ms"],
             "step_alg_bytes": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4),
             "step_frac": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4) / (total / args.steps) / 1e9 / peak,
@@ -281,10 +281,10 @@ def main():
             line["variants"] = variants(B, ops, dev, peak)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            best, med, times = cpu_reference_rate(128, 6, threads)
+            best, med, times = cpu_reference_rate(256, 8, threads)
             line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port", "median": med,
-                                    "sample": f"128 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
-                                              f"best of 6 after 1 warm-up, {sum(times):.1f} s CPU wall"}
+                                    "sample": f"256 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
+                                              f"best of 8 after 1 warm-up, {sum(times):.1f} s CPU wall"}
             b1, _, t1 = cpu_reference_rate(8, 3, 1)
             line["cpu_baseline"]["single_thread"] = {"value": b1, "cores": 1, "sample": "8 images, best of 3"}
     if rank == 0:
