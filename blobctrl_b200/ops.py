@@ -35,6 +35,8 @@ def canonical_blobs(xs, ys, covs, sizes) -> Tuple[torch.Tensor, torch.Tensor, to
     dev = covs.device
 
     def centre(t, name):
+        if torch.is_tensor(t) and t.shape == (n, m) and t.dtype == pdt and t.device == dev and t.is_contiguous():
+            return t                                        # already canonical: no torch ops on the latency path
         t = torch.as_tensor(t, device=dev)
         if t.ndim == 0:
             t = t.reshape(1)
@@ -44,6 +46,9 @@ def canonical_blobs(xs, ys, covs, sizes) -> Tuple[torch.Tensor, torch.Tensor, to
             raise RuntimeError(f"{name} must be [N, M], got {tuple(t.shape)}")
         return t.to(pdt).expand(n, m).contiguous()
 
+    if (torch.is_tensor(sizes) and sizes.shape == (n, m) and sizes.dtype == torch.float32 and sizes.device == dev
+            and sizes.is_contiguous() and covs.dtype == pdt and covs.is_contiguous()):
+        return centre(xs, "xs"), centre(ys, "ys"), covs, sizes, n, m
     sizes = torch.as_tensor(sizes, device=dev)
     if sizes.ndim == 3:
         sizes = sizes.squeeze(-1)
@@ -60,6 +65,11 @@ def render_scores(xs, ys, covs, sizes, height: int, width: int, select: str = "a
     xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
     if out_dtype is None:
         out_dtype = covs.dtype if covs.dtype in (torch.float32, torch.float64) + _HALF else torch.float32
+    if n > 65535:                                           # grid.y limit of the stand-alone kernel: split the batch
+        parts = [render_scores(xs[i:i + 65535], ys[i:i + 65535], covs_c[i:i + 65535], sizes[i:i + 65535], height, width,
+                               select, want_raw, want_composed, out_dtype, composite_mode) for i in range(0, n, 65535)]
+        cat = lambda j: torch.cat([p[j] for p in parts]) if parts[0][j] is not None else None
+        return cat(0), cat(1)
     ksel = {"all": m + 1, "fg": m, "bg": 1}[select]
     dev = covs_c.device
     composed = torch.empty((n, ksel, height, width), dtype=out_dtype, device=dev) if want_composed else None
