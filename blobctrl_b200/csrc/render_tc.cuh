@@ -33,6 +33,19 @@
 #include "common.cuh"
 
 // compile-time tuning knobs (scripts/ab_variants.py builds variants and A/Bs them in one process)
+// ablation switches (measurement only — they change the results): which role bounds the pipeline?
+#ifndef BS_ABL_NO_EPI_STORE
+#define BS_ABL_NO_EPI_STORE 0   // epilogue drains TMEM but skips the global stores
+#endif
+#ifndef BS_ABL_NO_COMP_STORE
+#define BS_ABL_NO_COMP_STORE 0  // stages 1+2 skip the composed-map global stores
+#endif
+#ifndef BS_ABL_NO_COMPUTE
+#define BS_ABL_NO_COMPUTE 0     // stages 1+2 skip the blob evaluation (opacity := 0.01)
+#endif
+#ifndef BS_ABL_NO_MMA
+#define BS_ABL_NO_MMA 0         // the MMA warp issues no tcgen05.mma (only the commits)
+#endif
 #ifndef BS_RNA_CUSTOM
 #define BS_RNA_CUSTOM 1
 #endif
@@ -242,7 +255,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       // =============================== stages 1+2 + operand staging ===============================
       // 8 warps: two per TMEM lane quarter.  Warp (half, q) owns pixels q*32..q*32+31 of the tile and one of
       // two contiguous blob ranges: half 0 the front (high-index) range, half 1 the back range + background.
-      const int ctid = threadIdx.x;                 // 0..255
+      const int ctid = warp * 32 + lane;            // 0..255 over the compute warps
       const int half = warp >> 2, q = warp & 3;
       const int px = q * 32 + lane;                 // pixel within the tile == TMEM lane
       asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
@@ -357,7 +370,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           for (; k < k_hi; ++k) my[k] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)k * p.sk)) : 0.0f;
         } else {
           float T = 1.0f;
-          const bool wr = comp != nullptr && live;
+          const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE;
           const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
           OT* const comp_px = comp + pix;                 // this pixel in plane 0; plane k is + k*P
           int m = m_hi;
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           for (; m >= m_lo + 8; m -= 8) {
             float s[8], d[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] = blob_opacity_pd(coef[m - 1 - j], xf, yf);
+            for (int j = 0; j < 8; ++j) s[j] = BS_ABL_NO_COMPUTE ? 0.01f : blob_opacity_pd(coef[m - 1 - j], xf, yf);
             OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -495,14 +508,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
               OT* oc = o + (size_t)cc * P;                       // chunk base; the 32 planes are immediates when kP > 0
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(ra[j])));
+                if (live && !BS_ABL_NO_EPI_STORE) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(ra[j])));
               tmem_wait_ld();
               if (cc + 32 < c_half) {
                 if (cc + 64 < c_half) tmem_ld32(taddr + cc + 64, ra);
                 oc += (size_t)32 * P;
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (live) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(rb[j])));
+                  if (live && !BS_ABL_NO_EPI_STORE) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(rb[j])));
                 tmem_wait_ld();
               }
             }
@@ -540,12 +553,12 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
               const uint32_t b_addr = b_base + (uint32_t)(2 * ks) * lbo + (uint32_t)(h * c_half) * 16u;
               const uint64_t b_hi = make_b_desc(b_addr, lbo, sbo);
               const uint32_t a_hi = tmem_a + (uint32_t)(ks * 8);
-              umma_ts<kTf32>(d_addr, a_hi, b_hi, idesc, acc);
+              if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi, b_hi, idesc, acc);
               acc = 1;
               if constexpr (kTf32) {
                 const uint64_t b_lo = make_b_desc(b_addr + (uint32_t)b_bytes, lbo, sbo);
-                umma_ts<kTf32>(d_addr, a_hi, b_lo, idesc, 1u);
-                umma_ts<kTf32>(d_addr, a_hi + (uint32_t)a_cols, b_hi, idesc, 1u);
+                if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi, b_lo, idesc, 1u);
+                if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi + (uint32_t)a_cols, b_hi, idesc, 1u);
               }
             }
             tc_commit(&bars->d_full[h]);
