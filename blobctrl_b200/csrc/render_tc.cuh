@@ -453,7 +453,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float w = live ? wv[j] : 0.0f;
+              const float w = wv[j];      // rows of pixels past the image end are never stored: no masking needed
               const float h = rna_tf32(w);
               hi[j] = __float_as_uint(h);
               lo[j] = __float_as_uint(rna_tf32(w - h));
@@ -471,10 +471,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             const float wv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float w0 = live ? wv[2 * j] : 0.0f;
-              const float w1 = live ? wv[2 * j + 1] : 0.0f;
-              OT lo16 = Cvt<OT>::from(w0), hi16 = Cvt<OT>::from(w1);
-              pk[j] = (uint32_t)(*reinterpret_cast<uint16_t*>(&lo16)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&hi16)) << 16);
+              // one packed convert per column (low half = even k)
+              if constexpr (std::is_same<OT, __nv_bfloat16>::value) {
+                const __nv_bfloat162 t = __floats2bfloat162_rn(wv[2 * j], wv[2 * j + 1]);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+              } else {
+                const __half2 t = __floats2half2_rn(wv[2 * j], wv[2 * j + 1]);
+                pk[j] = *reinterpret_cast<const uint32_t*>(&t);
+              }
             }
             tmem_st8(tmem_a + lane_addr + g * 8, pk);
           }

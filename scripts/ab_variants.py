@@ -8,7 +8,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "cur": "",
-    "compute_high_prio": "-DBS_ROLE_ORDER=1",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 
