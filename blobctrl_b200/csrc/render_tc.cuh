@@ -174,6 +174,21 @@ __device__ __forceinline__ float rna_tf32(float x) {
 #endif
 }
 
+// Two values bound for two different planes.  For 16-bit maps one packed convert (F2FP) serves both stores —
+// F2FP + PRMT + 2 STG per pair instead of 2 x (F2FP + PRMT + STG).
+template <typename OT>
+__device__ __forceinline__ void store_pair(OT* p0, OT* p1, float a, float b, bool pred) {
+  if constexpr (std::is_same<OT, __nv_bfloat16>::value) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    if (pred) { __stcs(p0, __low2bfloat16(t)); __stcs(p1, __high2bfloat16(t)); }
+  } else if constexpr (std::is_same<OT, __half>::value) {
+    const __half2 t = __floats2half2_rn(a, b);
+    if (pred) { __stcs(p0, __low2half(t)); __stcs(p1, __high2half(t)); }
+  } else {
+    if (pred) { __stcs(p0, (OT)a); __stcs(p1, (OT)b); }
+  }
+}
+
 struct RenderTcParams {
   const float* xs; const float* ys; const float* covs; const float* sizes;
   const void* scores; long long sn, sk, sp;   // kFromScores: precomputed weights [N,K,P] with element strides
@@ -393,8 +408,9 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
             for (int j = 0; j < 8; ++j) {
               d[j] = s[j] * T;
               T = fmaf(-s[j], T, T);
-              if (wr_now) __stcs(cp - (ptrdiff_t)j * P, Cvt<OT>::from(d[j]));
             }
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) store_pair<OT>(cp - (ptrdiff_t)j * P, cp - (ptrdiff_t)(j + 1) * P, d[j], d[j + 1], wr_now);
             *reinterpret_cast<float4*>(my + m - 7) = make_float4(d[7], d[6], d[5], d[4]);
             *reinterpret_cast<float4*>(my + m - 3) = make_float4(d[3], d[2], d[1], d[0]);
           }
@@ -423,11 +439,9 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
                 float4 v4 = *reinterpret_cast<const float4*>(my + k - 3);
                 v4.x *= c; v4.y *= c; v4.z *= c; v4.w *= c;
                 *reinterpret_cast<float4*>(my + k - 3) = v4;
-                if (wr) {
-                  OT* const cp = comp_px + (size_t)k * P;
-                  __stcs(cp, Cvt<OT>::from(v4.w)); __stcs(cp - (ptrdiff_t)P, Cvt<OT>::from(v4.z));
-                  __stcs(cp - (ptrdiff_t)2 * P, Cvt<OT>::from(v4.y)); __stcs(cp - (ptrdiff_t)3 * P, Cvt<OT>::from(v4.x));
-                }
+                OT* const cp = comp_px + (size_t)k * P;
+                store_pair<OT>(cp, cp - (ptrdiff_t)P, v4.w, v4.z, wr);
+                store_pair<OT>(cp - (ptrdiff_t)2 * P, cp - (ptrdiff_t)3 * P, v4.y, v4.x, wr);
               }
               for (; k >= 1; --k) {
                 const float v = my[k] * c;
@@ -511,15 +525,17 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
               if (cc + 32 < c_half) tmem_ld32(taddr + cc + 32, rb);
               OT* oc = o + (size_t)cc * P;                       // chunk base; the 32 planes are immediates when kP > 0
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (live && !BS_ABL_NO_EPI_STORE) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(ra[j])));
+              for (int j = 0; j < 32; j += 2)
+                store_pair<OT>(oc + (size_t)j * P, oc + (size_t)(j + 1) * P, __uint_as_float(ra[j]), __uint_as_float(ra[j + 1]),
+                               live && !BS_ABL_NO_EPI_STORE);
               tmem_wait_ld();
               if (cc + 32 < c_half) {
                 if (cc + 64 < c_half) tmem_ld32(taddr + cc + 64, ra);
                 oc += (size_t)32 * P;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (live && !BS_ABL_NO_EPI_STORE) __stcs(oc + (size_t)j * P, Cvt<OT>::from(__uint_as_float(rb[j])));
+                for (int j = 0; j < 32; j += 2)
+                  store_pair<OT>(oc + (size_t)j * P, oc + (size_t)(j + 1) * P, __uint_as_float(rb[j]), __uint_as_float(rb[j + 1]),
+                                 live && !BS_ABL_NO_EPI_STORE);
                 tmem_wait_ld();
               }
             }
