@@ -149,11 +149,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 // callers) take the general quadratic form qa*dx^2 + qb*dx*dy + qc*dy^2 instead.
 struct __align__(16) BlobCoef {
   float cx_hi, cx_lo, cy_hi, cy_lo;
-  float p, r, t;      // whitened (or qa, qb, qc when flags & kGeneral)
-  uint32_t flags;
+  float p, r, t;      // whitened (or qa, qb, qc when c0 == kC0General)
+  float c0;           // exponent offset AND blob kind: see below
 };
-constexpr uint32_t kGated = 1u;    // sizes < 0.5 -> score 1e-6  (utils.py:165-172)
-constexpr uint32_t kGeneral = 2u;  // covariance not PD: use the plain quadratic form
+// c0 is the constant folded into the exponent, q' - 1 = u^2 + v^2 + c0, and doubles as the blob's kind:
+//   kC0Normal  (-1)      positive-definite blob
+//   kC0Gated   (> 0)     non-existent blob (sizes < 0.5 -> score 1e-6, utils.py:165-172): p = r = t = 0 and
+//                        c0 = log2(1e6 - 0.5), so the branch-free form yields 1/(0.5 + 2^c0) = 1e-6 (to ~3e-7 relative)
+//                        with no select; the branching forms test c0 > 0 and return the exact constant
+//   kC0General (-2)      covariance not positive definite: p, r, t hold the plain quadratic form
+constexpr float kC0Normal = -1.0f, kC0General = -2.0f, kC0Gated = 19.931567847f;
+__device__ __forceinline__ bool coef_gated(const BlobCoef& c) { return c.c0 > 0.0f; }
+__device__ __forceinline__ bool coef_general(const BlobCoef& c) { return c.c0 == kC0General; }
 
 __device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double c00, double c01, double c10,
                                                    double c11, float size, int H, int W) {
@@ -168,14 +175,14 @@ __device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double 
   const double A = l2e * (c11 / det) / ((double)W * (double)W);
   const double B = l2e * (-0.5 * (c01 + c10) / det) / ((double)W * (double)H);
   const double C = l2e * (c00 / det) / ((double)H * (double)H);
-  o.flags = (size < 0.5f) ? kGated : 0u;
   const double schur = A - (B * B) / C;
-  if (C > 0.0 && schur > 0.0) {
+  if (size < 0.5f) {
+    o.p = o.r = o.t = 0.0f; o.c0 = kC0Gated;
+  } else if (C > 0.0 && schur > 0.0) {
     const double t = sqrt(C);
-    o.t = (float)t; o.r = (float)(B / t); o.p = (float)sqrt(schur);
+    o.t = (float)t; o.r = (float)(B / t); o.p = (float)sqrt(schur); o.c0 = kC0Normal;
   } else {
-    o.p = (float)A; o.r = (float)(2.0 * B); o.t = (float)C;
-    o.flags |= kGeneral;
+    o.p = (float)A; o.r = (float)(2.0 * B); o.t = (float)C; o.c0 = kC0General;
   }
   return o;
 }
@@ -202,8 +209,8 @@ __device__ __forceinline__ BlobCoef make_blob_coef_ellipse(double xc, double yc,
   const double m10 = D * sn / (a * (double)W), m11 = D * cs / (a * (double)H);
   const double Bq = m00 * m01 + m10 * m11, Cq = m01 * m01 + m11 * m11;
   const double t = sqrt(Cq);
-  o.t = (float)t; o.r = (float)(Bq / t); o.p = (float)(fabs(m00 * m11 - m01 * m10) / t);
-  o.flags = (size < 0.5f) ? kGated : 0u;
+  o.t = (float)t; o.r = (float)(Bq / t); o.p = (float)(fabs(m00 * m11 - m01 * m10) / t); o.c0 = kC0Normal;
+  if (size < 0.5f) { o.p = o.r = o.t = 0.0f; o.c0 = kC0Gated; }
   return o;
 }
 
@@ -229,23 +236,15 @@ __device__ __forceinline__ float blob_opacity_pd(const BlobCoef& c, float xf, fl
   const float dx = (xf - c.cx_hi) - c.cx_lo;
   const float u = c.p * dx;
   const float v = fmaf(c.r, dx, c.t * dy);
-#ifndef BS_FOLD
-#define BS_FOLD 1
-#endif
-#if BS_FOLD
-  const float s = opacity_from_q2m1(fmaf(u, u, fmaf(v, v, -1.0f)));
-#else
-  const float s = opacity_from_q2(fmaf(u, u, v * v));
-#endif
-  return (c.flags & kGated) ? 1e-6f : s;
+  return opacity_from_q2m1(fmaf(u, u, fmaf(v, v, c.c0)));   // gated blobs: u = v = 0, c0 = log2(1e6 - 0.5)
 }
 
 // raw opacity of one blob at one pixel (stage 1 + gate)
 __device__ __forceinline__ float blob_opacity(const BlobCoef& c, float xf, float yf) {
-  if (c.flags & kGated) return 1e-6f;
+  if (coef_gated(c)) return 1e-6f;
   const float dy = (yf - c.cy_hi) - c.cy_lo;
   const float dx = (xf - c.cx_hi) - c.cx_lo;
-  if (!(c.flags & kGeneral)) {
+  if (!coef_general(c)) {
     const float u = c.p * dx;
     const float v = fmaf(c.r, dx, c.t * dy);
     return opacity_from_q2(fmaf(u, u, v * v));

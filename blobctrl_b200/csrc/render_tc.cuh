@@ -281,7 +281,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
         const float* c = p.covs + 4 * b;
         const BlobCoef bc = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
                                            (double)c[3], p.sizes[b], p.H, p.W);
-        my_general |= bc.flags & kGeneral;
+        my_general |= coef_general(bc) ? 1u : 0u;
         coef[i] = bc;
       }
       if (unit_it == 0) {   // stash columns that are never written (k' < kTcKOff, k' >= K + kTcKOff) stay zero for the whole kernel

@@ -73,13 +73,13 @@ scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys
       const BlobCoef c = coef[i];
       const int k = lo + i + 1;
       float s[V];
-      if (c.flags & kGated) {
+      if (coef_gated(c)) {
 #pragma unroll
         for (int j = 0; j < V; ++j) s[j] = 1e-6f;
       } else {
         const float dy = (yf - c.cy_hi) - c.cy_lo;
         const float dx0 = (xf - c.cx_hi) - c.cx_lo;
-        if (!(c.flags & kGeneral)) {
+        if (!coef_general(c)) {
           const float u0 = c.p * dx0;
           const float v0 = fmaf(c.r, dx0, c.t * dy);
 #pragma unroll
