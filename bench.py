@@ -281,10 +281,10 @@ def main():
             line["variants"] = variants(B, ops, dev, peak)
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            best, med, times = cpu_reference_rate(256, 8, threads)
+            best, med, times = cpu_reference_rate(256, 14, threads)
             line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port", "median": med,
                                     "sample": f"256 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
-                                              f"best of 8 after 1 warm-up, {sum(times):.1f} s CPU wall"}
+                                              f"best of 14 after 1 warm-up, {sum(times):.1f} s CPU wall"}
             b1, _, t1 = cpu_reference_rate(8, 3, 1)
             line["cpu_baseline"]["single_thread"] = {"value": b1, "cores": 1, "sample": "8 images, best of 3"}
     if rank == 0:
