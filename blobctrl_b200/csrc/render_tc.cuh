@@ -131,6 +131,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+// 16 lanes x 32 bit x 2, 16 repeats: threads 0-15 get columns c .. c+15 of the 16 lanes at the address's lane,
+// threads 16-31 columns c+16 .. c+31 of the same lanes (layout measured with scripts/probes/tmem_ld_layout.cu).
+__device__ __forceinline__ void tmem_ld_16x32bx2_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x32bx2.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16], 16;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -189,6 +199,14 @@ __device__ __forceinline__ void store_pair(OT* p0, OT* p1, float a, float b, boo
   }
 }
 
+// One 32-channel block of the pixel-pair epilogue (float maps): r[j] / r[16 + j] are channel j of this thread's two
+// adjacent pixels, stored as one 64-bit word; a half-warp covers one whole 128-byte line of a channel plane.
+__device__ __forceinline__ void store_pixel_pairs(float* oc, size_t P, const uint32_t* r, bool pred) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (pred) __stcs(reinterpret_cast<float2*>(oc + (size_t)j * P), make_float2(__uint_as_float(r[j]), __uint_as_float(r[16 + j])));
+}
+
 struct RenderTcParams {
   const float* xs; const float* ys; const float* covs; const float* sizes;
   const void* scores; long long sn, sk, sp;   // kFromScores: precomputed weights [N,K,P] with element strides
@@ -198,6 +216,7 @@ struct RenderTcParams {
   int c_tile, c_chunks;   // channels per work unit (multiple of 32, <= 320); ceil(C / c_tile)
   int tiles_per_image, tiles_per_unit, segs;  // 128-pixel tiles; unit = (image, chunk, tile segment)
   int total_units;
+  int pair_ok;            // float maps: grid planes allow aligned 2-pixel stores (P even, base 8-byte aligned)
 };
 
 struct TcBarriers {
@@ -272,7 +291,11 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       // two contiguous blob ranges: half 0 the front (high-index) range, half 1 the back range + background.
       const int ctid = warp * 32 + lane;            // 0..255 over the compute warps
       const int half = warp >> 2, q = warp & 3;
-      const int px = q * 32 + lane;                 // pixel within the tile == TMEM lane
+      const int px = q * 32 + lane;                 // TMEM lane / stash row of this thread
+      // Its pixel within the tile.  Float maps: lanes L and L+16 of a quarter hold ADJACENT pixels, so the epilogue's
+      // 16x32bx2 TMEM loads hand one thread two consecutive pixels of a channel (64-bit stores, half the store
+      // instructions).  A warp still covers the same 32 consecutive pixels, so the composed-map stores stay coalesced.
+      const int ppx = kTf32 ? q * 32 + ((lane & 15) << 1) + (lane >> 4) : px;
       asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
       uint32_t my_general = 0;
       if constexpr (!kFromScores)
@@ -363,7 +386,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
-        const int pix = (t_lo + t) * kTcTileM + px;
+        const int pix = (t_lo + t) * kTcTileM + ppx;
         const bool live = pix < P;
         const int y = live ? pix / p.W : 0;
         const float xf = (float)(live ? pix - y * p.W : 0), yf = (float)y;
@@ -507,7 +530,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       const int q = warp - kTcComputeWarps;        // TMEM lane quarter
       OT* out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
-        const int pix = (t_lo + t) * kTcTileM + q * 32 + lane;
+        // same lane -> pixel map as stages 1+2
+        const int pix = (t_lo + t) * kTcTileM + q * 32 + (kTf32 ? ((lane & 15) << 1) + (lane >> 4) : lane);
         const bool live = pix < P;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
@@ -516,8 +540,34 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
           OT* const o = out + (size_t)(h * c_half) * P + pix;   // this pixel in the half's first channel plane
           const int ch_left = p.C - (c0 + h * c_half);          // valid channels in this half (may exceed c_half)
-          if (ch_left >= c_half && (c_half & 31) == 0) {
-            // fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
+          bool done = false;
+          if constexpr (kTf32) {
+            if (p.pair_ok && ch_left >= c_half && (c_half & 31) == 0) {
+              // float fast path: thread t owns pixels 2*(t%16), +1 of channels 16*(t/16) + j of each 32-channel block
+              // (two 16-lane loads); the next block's loads are in flight while this one is stored
+              const int pix2 = (t_lo + t) * kTcTileM + q * 32 + ((lane & 15) << 1);
+              const bool live2 = pix2 < P && !BS_ABL_NO_EPI_STORE;
+              const uint32_t tb = taddr + (16u << 16);
+              float* const o2 = reinterpret_cast<float*>(out) + (size_t)(h * c_half + ((lane >> 4) << 4)) * P + pix2;
+              uint32_t ra[32], rb[32];
+              tmem_ld_16x32bx2_x16(taddr, ra); tmem_ld_16x32bx2_x16(tb, ra + 16);
+              tmem_wait_ld();
+              for (int cc = 0; cc < c_half; cc += 64) {
+                if (cc + 32 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 32, rb); tmem_ld_16x32bx2_x16(tb + cc + 32, rb + 16); }
+                store_pixel_pairs(o2 + (size_t)cc * P, (size_t)P, ra, live2);
+                tmem_wait_ld();
+                if (cc + 32 < c_half) {
+                  if (cc + 64 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 64, ra); tmem_ld_16x32bx2_x16(tb + cc + 64, ra + 16); }
+                  store_pixel_pairs(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2);
+                  tmem_wait_ld();
+                }
+              }
+              done = true;
+            }
+          }
+          if (done) {
+          } else if (!kTf32 && ch_left >= c_half && (c_half & 31) == 0) {
+            // 16-bit fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
             tmem_wait_ld();
@@ -670,7 +720,9 @@ static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
     sm_dev = dev;
   }
   const int grid = std::min(sm_count, p.total_units);
-  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(p);
+  RenderTcParams pq = p;
+  pq.pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
+  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(pq);
   BS_CUDA(cudaGetLastError());
   return 0;
 }

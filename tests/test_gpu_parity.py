@@ -566,3 +566,33 @@ def test_residual_injection_bit_exact(dtype):
         assert torch.equal(got, want)
     sq = torch.randn(2, 8, h, h, generator=g).to(DEV).to(dtype); rq = torch.randn(2, 8, h, h, generator=g).to(DEV).to(dtype)
     assert torch.equal(inject_residual(sq.clone(), rq, 0.7), sq + rq * 0.7)    # square map: whole width (:1216)
+
+
+@pytest.mark.parametrize("h,w,c,dtype,rel", [
+    (7, 9, 64, torch.float32, 1e-5),       # odd pixel count: no 2-pixel stores, partial tile
+    (6, 11, 96, torch.float32, 1e-5),      # even pixel count, not a multiple of 4, partial tile
+    (20, 20, 352, torch.float32, 1e-5),    # two channel chunks, ragged second chunk (generic drain)
+    (16, 16, 320, torch.float32, 1e-5),    # plane-stride specialisation 256
+    (7, 9, 64, torch.bfloat16, 1e-2), (10, 13, 96, torch.float16, 2e-3)])
+def test_fused_render_epilogue_paths(h, w, c, dtype, rel):
+    """blobsplat_render's drain paths: pixel-pair vector stores (float maps), the per-lane 16-bit path and the generic
+    path, on ragged tiles, plus an output buffer that is only 4-byte aligned (vector stores must not be used)."""
+    from blobctrl_b200 import ops
+    n, m = 3, 19
+    syn = blob_oracle.synthetic_blobs(n, m, seed=h * 100 + w, c=c)
+    raw = blob_oracle.raw_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], h, w, np.float64)
+    _, dref = blob_oracle.composite(raw)
+    want_d = np.moveaxis(dref, -1, 1)
+    b = _blob(syn)
+    feats = _cuda(syn["features"]).to(dtype)
+    want_g = blob_oracle.splat_features_from_scores(want_d, _np(feats).astype(np.float64), None, channels_last=False)
+    comp, grid = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w)
+    close_scaled(_np(comp), want_d, rel, f"composed {h}x{w}")
+    close_scaled(_np(grid), want_g, 2 * rel, f"grid {h}x{w} C={c}")
+    # same call into a buffer offset by one element: grid base not 8/16-byte aligned
+    store = torch.zeros(n * c * h * w + 1, dtype=dtype, device=DEV)
+    grid2 = store[1:].view(n, c, h, w)
+    comp2 = torch.empty_like(comp)
+    ops.render_fused_into(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w, comp2, grid2)
+    assert torch.equal(grid2, grid) and torch.equal(comp2, comp)
+    assert float(store[0]) == 0.0
