@@ -44,8 +44,10 @@ def run():
                                     f.data_ptr(), code, 1024, 64, 64, 64, 320, comp.data_ptr(), grid.data_ptr(), code, 0, st)
             assert rc == 0
         res = {n: [] for n in libs}
-        for rnd in range(5):
-            for n, L in libs.items():
+        for rnd in range(6):
+            order = list(libs.items())
+            order = order[rnd % len(order):] + order[:rnd % len(order)]     # rotate: no variant always runs first
+            for n, L in order:
                 for _ in range(3): call(L)
                 torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -54,7 +56,11 @@ def run():
                 e1.record(); torch.cuda.synchronize()
                 res[n].append(round(e0.elapsed_time(e1) / 20, 4))
         print(dtype)
-        for n, v in res.items(): print(f"  {n:18s} {v}  median {sorted(v)[len(v)//2]}")
+        for n, v in res.items():
+            call(libs[n]); torch.cuda.synchronize()      # stage-3 error of this variant against float64 on its own weights
+            ref = torch.einsum("nkp,nkc->ncp", comp[:8].double().flatten(2), f[:8].double())
+            err = ((grid[:8].double().flatten(2) - ref).abs().max() / ref.abs().max()).item()
+            print(f"  {n:18s} {v}  median {sorted(v)[len(v)//2]}  stage-3 err/scale {err:.2e}")
         for tn in [n for n in libs if n.startswith("timing")]:
             call(libs[tn]); torch.cuda.synchronize()
             buf = (ctypes.c_ulonglong * 48)()
