@@ -20,7 +20,7 @@ ABI_VERSION = 1
 
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libblobsplat.so")
+LIB_PATH = os.environ.get("BLOBSPLAT_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libblobsplat.so")   # BLOBSPLAT_LIB: A/B builds (scripts/ab_variants.py)
 
 
 class BlobSplatLibraryError(RuntimeError):

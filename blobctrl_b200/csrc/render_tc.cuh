@@ -46,6 +46,9 @@
 #ifndef BS_ABL_NO_MMA
 #define BS_ABL_NO_MMA 0         // the MMA warp issues no tcgen05.mma (only the commits)
 #endif
+#ifndef BS_STAGE_COST
+#define BS_STAGE_COST 3        // cost of staging one unit's operands, in tiles (loads queue behind the saturated store stream)
+#endif
 #ifndef BS_RNA_CUSTOM
 #define BS_RNA_CUSTOM 1
 #endif
@@ -214,10 +217,16 @@ struct RenderTcParams {
   int N, M, H, W, C;
   int K, Kp;              // K = M + 1; Kp = K rounded up to the MMA k-step (8 tf32 / 16 f16)
   int c_tile, c_chunks;   // channels per work unit (multiple of 32, <= 320); ceil(C / c_tile)
-  int tiles_per_image, tiles_per_unit, segs;  // 128-pixel tiles; unit = (image, chunk, tile segment)
-  int total_units;
+  int tiles_per_image;    // 128-pixel tiles per image
+  int whole_runs;         // schedule: whole (image, chunk) runs round-robin vs contiguous equal tile ranges
+  int total_tiles;        // N * c_chunks * tiles_per_image, linear index ((n * c_chunks + chunk) * tiles_per_image + tile)
   int pair_ok;            // float maps: grid planes allow aligned 2-pixel stores (P even, base 8-byte aligned)
 };
+
+// First tile of CTA i's range under the equal-shares schedule.
+__host__ __device__ __forceinline__ int tc_range_begin(int total_tiles, int i, int ctas) {
+  return (int)((long long)total_tiles * i / ctas);
+}
 
 struct TcBarriers {
   uint64_t a_full, a_free, b_full, b_free, d_full[2], d_empty[2];
@@ -275,15 +284,22 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   int unit_it = 0;      // units processed by this CTA so far
   int tile_it = 0;      // tiles processed by this CTA so far (barrier phases)
 
-  for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++unit_it) {
-    const int per_image = p.c_chunks * p.segs;
-    const int n = unit / per_image;
-    const int rem = unit - n * per_image;
-    const int chunk = rem / p.segs, seg = rem - chunk * p.segs;
+  // Work distribution over the linear tile sequence; a work unit = a run of tiles of one (image, channel chunk), whose
+  // operands (blob coefficients, B) are staged once.  Two schedules, chosen on the host (fill_tc_units):
+  //   whole_runs  CTA i takes the whole runs i, i + gridDim.x, ... (large batches: fewest stagings, CTAs in lock-step)
+  //   otherwise   the sequence is cut into gridDim.x contiguous, equally long ranges (+-1 tile), which a CTA walks as
+  //               partial runs (small batches: balance matters more than the extra stagings)
+  const int g_end = p.whole_runs ? p.total_tiles : tc_range_begin(p.total_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
+  for (int g = p.whole_runs ? (int)blockIdx.x * p.tiles_per_image : tc_range_begin(p.total_tiles, (int)blockIdx.x, (int)gridDim.x);
+       g < g_end; ++unit_it) {
+    const int img_chunk = g / p.tiles_per_image;
+    const int n = img_chunk / p.c_chunks;
+    const int chunk = img_chunk - n * p.c_chunks;
     const int c0 = chunk * p.c_tile;
-    const int t_lo = seg * p.tiles_per_unit;
-    const int t_hi = min(t_lo + p.tiles_per_unit, p.tiles_per_image);
-    const int ntiles = t_hi - t_lo;
+    const int t_lo = g - img_chunk * p.tiles_per_image;
+    const int ntiles = min(p.tiles_per_image - t_lo, g_end - g);
+    g += ntiles;
+    if (p.whole_runs) g += ((int)gridDim.x - 1) * p.tiles_per_image;
 
     if (warp < kTcComputeWarps) {
       // =============================== stages 1+2 + operand staging ===============================
@@ -688,20 +704,23 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   p.c_tile = pl.c_tile; p.c_chunks = (C + pl.c_tile - 1) / pl.c_tile;
   const int P = H * W;
   p.tiles_per_image = (P + kTcTileM - 1) / kTcTileM;
-  // Work units: whole images when there are plenty; otherwise split each image's tiles so that every SM gets work.
+  const long long total = (long long)N * p.c_chunks * p.tiles_per_image;
+  if (total > 0x7fffffffll) BS_UNSUPPORTED("too many tiles for one launch");
+  p.total_tiles = (int)total;
+  // pick the cheaper partition under the cost model: a tile = 1, staging a unit's operands = BS_STAGE_COST tiles
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long base_units = (long long)N * p.c_chunks;
-  int segs = 1;
-  if (base_units < 4ll * sms) {
-    segs = (int)std::min<long long>(p.tiles_per_image, (4ll * sms + base_units - 1) / base_units);
-    if (p.tiles_per_image / segs < 4) segs = std::max(1, p.tiles_per_image / 4);   // keep >= 4 tiles per B load
+  const int ctas = std::min(sms, p.total_tiles);
+  long long ranges = 0;                                        // worst CTA under equal tile ranges
+  for (int i = 0; i < ctas; ++i) {
+    const int lo = tc_range_begin(p.total_tiles, i, ctas), hi = tc_range_begin(p.total_tiles, i + 1, ctas);
+    if (hi <= lo) continue;
+    const int units = (hi - 1) / p.tiles_per_image - lo / p.tiles_per_image + 1;
+    ranges = std::max<long long>(ranges, (hi - lo) + 2ll * BS_STAGE_COST * units);   // staggered stagings queue behind other CTAs' stores: twice the cost
   }
-  p.tiles_per_unit = (p.tiles_per_image + segs - 1) / segs;
-  p.segs = (p.tiles_per_image + p.tiles_per_unit - 1) / p.tiles_per_unit;
-  const long long total = base_units * p.segs;
-  if (total > 0x7fffffffll) BS_UNSUPPORTED("too many work units");
-  p.total_units = (int)total;
+  const long long runs = total / p.tiles_per_image;
+  const long long whole = ctas > 0 ? (runs + ctas - 1) / ctas * (p.tiles_per_image + BS_STAGE_COST) : 0;
+  p.whole_runs = whole <= ranges ? 1 : 0;
   return 0;
 }
 
@@ -719,7 +738,7 @@ static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
     BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     sm_dev = dev;
   }
-  const int grid = std::min(sm_count, p.total_units);
+  const int grid = std::min(sm_count, p.total_tiles);
   RenderTcParams pq = p;
   pq.pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
   render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(pq);
@@ -731,6 +750,7 @@ template <typename FT, typename OT, bool kTf32, int kHalves, bool kFromScores>
 static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
   if constexpr (kHalves == 2) {   // plane-stride specialisations for BlobNet's latent resolutions (64/32/16)
     switch (p.H * p.W) {
+      case 64: if constexpr (kFromScores) return launch_tc_p<FT, OT, kTf32, kHalves, 64, kFromScores>(p, smem, st); else break;
       case 4096: return launch_tc_p<FT, OT, kTf32, kHalves, 4096, kFromScores>(p, smem, st);
       case 1024: return launch_tc_p<FT, OT, kTf32, kHalves, 1024, kFromScores>(p, smem, st);
       case 256: return launch_tc_p<FT, OT, kTf32, kHalves, 256, kFromScores>(p, smem, st);
