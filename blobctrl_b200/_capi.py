@@ -48,6 +48,7 @@ SIGNATURES = {
     "blobsplat_resize_bilinear": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_pyramid": [_P, ctypes.POINTER(_P), _I, _I, _I, _I, _I, _P],
     "blobsplat_feature_splat": [_P, _L, _L, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "blobsplat_feature_splat_levels": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P],
     "blobsplat_conditioning_fill": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_residual_inject": [_P, _P, _P, ctypes.c_float, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_render": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
@@ -129,3 +130,16 @@ def stream_of(t: torch.Tensor):
 
 def dev_of(t: torch.Tensor) -> int:
     return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+_POISON = os.environ.get("BLOBSPLAT_POISON_OUTPUTS") == "1"
+
+
+def new_output(shape, dtype, device):
+    """Output buffer for a kernel that writes every element: uninitialised, or — BLOBSPLAT_POISON_OUTPUTS=1, set by the
+    GPU test-suite — NaN-filled, so that an element the kernel failed to write cannot pass a comparison by holding
+    stale data of an earlier, identical call from the caching allocator."""
+    import torch
+    if _POISON and dtype.is_floating_point:
+        return torch.full(tuple(shape), float("nan"), dtype=dtype, device=device)
+    return torch.empty(tuple(shape), dtype=dtype, device=device)

@@ -32,6 +32,9 @@ int feature_splat_fma_dispatch(const void*, int64_t, int64_t, int64_t, const voi
                                int, cudaStream_t);
 int feature_splat_tc_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int, int,
                               cudaStream_t);
+int feature_splat_levels_tc_dispatch(int, const void* const*, const int64_t*, const int64_t*, const int64_t*,
+                                     const void* const*, void* const*, int, int, const int*, const int*, const int*, int,
+                                     cudaStream_t);
 int render_tc_dispatch(const float*, const float*, const float*, const float*, const void*, int, int, int, int, int,
                        int, void*, void*, int, cudaStream_t);
 int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, int,
@@ -41,6 +44,9 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
 constexpr int kMaxBlobs = 1 << 20;
+#ifndef BS_FUSE_LEVELS_AUTO
+#define BS_FUSE_LEVELS_AUTO 0
+#endif
 
 static bool valid_dtype(int dt) { return dt >= BLOBSPLAT_F32 && dt <= BLOBSPLAT_F16; }
 
@@ -168,6 +174,42 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
                                      (cudaStream_t)stream);
   return feature_splat_fma_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
                                     (cudaStream_t)stream);
+}
+
+int blobsplat_feature_splat_levels(int n_levels, const void* const* scores, const int64_t* stride_n,
+                                   const int64_t* stride_k, const int64_t* stride_p, const void* const* features,
+                                   void* const* outs, int N, int K, const int* C, const int* H, const int* W, int dtype,
+                                   int engine, int device, void* stream) {
+  BS_CHECK_ARG(n_levels >= 0 && n_levels <= 16, "bad level count %d", n_levels);
+  if (n_levels == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(scores && stride_n && stride_k && stride_p && features && outs && C && H && W, "NULL level array");
+  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TENSOR, "bad engine %d", engine);
+  BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
+  // One launch for the whole pyramid when every level is a dense contraction with the same operand tiling
+  // (BlobNet's 640/1280-channel levels); otherwise level by level.  BS_FUSE_LEVELS_AUTO: whether AUTO fuses too —
+  // measured on cfg3 (profiles/render_tc_r1.md) the per-level launches with their compile-time plane strides win
+  // until operand staging overlaps across units, so AUTO stays level by level and TENSOR asks for the single launch.
+  bool fuse = N > 0 && n_levels >= 2 && n_levels <= 4 && dtype != BLOBSPLAT_F64 &&
+              (engine == BLOBSPLAT_ENGINE_TENSOR || (BS_FUSE_LEVELS_AUTO && engine == BLOBSPLAT_ENGINE_AUTO && K >= 12));
+  for (int i = 0; i < n_levels && fuse; ++i) {
+    const char* why = nullptr;
+    fuse = scores[i] && features[i] && outs[i] && C[i] >= 64 && H[i] >= 1 && W[i] >= 1 &&
+           (long long)H[i] * W[i] < (1ll << 31) && stride_k[i] >= 0 && stride_p[i] >= 1 && stride_n[i] >= 0 &&
+           render_tc_supported(K, C[i], H[i], W[i], dtype, dtype, &why);
+  }
+  if (fuse && N <= 65535 && K >= 1) {
+    DeviceGuard g(device);
+    if (g.status) return g.status;
+    const int rc = feature_splat_levels_tc_dispatch(n_levels, scores, stride_n, stride_k, stride_p, features, outs, N, K,
+                                                    C, H, W, dtype, (cudaStream_t)stream);
+    if (rc <= 0) return rc;     // 1 = the levels cannot share a launch
+  }
+  for (int i = 0; i < n_levels; ++i) {
+    const int rc = blobsplat_feature_splat(scores[i], stride_n[i], stride_k[i], stride_p[i], features[i], outs[i], N, K,
+                                           C[i], H[i], W[i], dtype, engine, device, stream);
+    if (rc != BLOBSPLAT_OK) return rc;
+  }
+  return BLOBSPLAT_OK;
 }
 
 int blobsplat_conditioning_fill(const void* scores, const void* features, void* out, int B, int K, int C, int h, int w,

@@ -228,6 +228,15 @@ __host__ __device__ __forceinline__ int tc_range_begin(int total_tiles, int i, i
   return (int)((long long)total_tiles * i / ctas);
 }
 
+// Kernel argument: one problem (the fused render, a single stage-3 splat) or up to kTcMaxLevels stage-3 problems of one
+// pyramid that share K, dtype and channel tile and run as ONE launch over the concatenated tile sequence.
+constexpr int kTcMaxLevels = 4;
+struct RenderTcLevels {
+  RenderTcParams lv[kTcMaxLevels];
+  int n_levels;
+  int tile_start[kTcMaxLevels + 1];   // first linear tile of each level; [n_levels] = total
+};
+
 struct TcBarriers {
   uint64_t a_full, a_free, b_full, b_free, d_full[2], d_empty[2];
   uint32_t tmem_base;
@@ -236,10 +245,12 @@ struct TcBarriers {
 // FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
 // kP: pixels per image when it is one of the common sizes (64^2, 32^2, 16^2), else 0 = runtime.  With a
 // compile-time plane stride every store of an unrolled group is [base + immediate]: no address arithmetic.
+// kP = -1: several pyramid levels in one launch (RenderTcLevels); every work unit reads its own level's shape.
 // kFromScores: the A operand comes from precomputed score maps in global memory (stand-alone stage 3,
 // splat_features_from_scores) instead of being rendered from blob parameters (stages 1+2).
 template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
-__global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const RenderTcParams p) {
+__global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const __grid_constant__ RenderTcLevels L) {
+  const RenderTcParams& p0 = L.lv[0];     // Kp, c_tile and the dtypes are the same for every level
   constexpr int kTcComputeWarps = 4 * kHalves;
   constexpr int kTcComputeThreads = kTcComputeWarps * 32;
   constexpr int kTcMmaWarp = kTcComputeWarps + 4;
@@ -250,11 +261,10 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   constexpr int kNumB = kTf32 ? 2 : 1;                             // hi + lo
   constexpr int kACols = kTf32 ? 1 : 2;                            // k elements per 32-bit TMEM column
 
-  const int P = kP > 0 ? kP : p.H * p.W;
-  const int c_half = p.c_tile >> 1;
-  const size_t b_bytes = (size_t)(p.Kp / kElemsPer16B) * p.c_tile * 16;   // one B copy
+  const int c_half = p0.c_tile >> 1;
+  const size_t b_bytes = (size_t)(p0.Kp / kElemsPer16B) * p0.c_tile * 16;   // one B copy
   unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
-  const int srow = p.Kp + 4;                                               // stash row stride (floats): conflict-free LDS/STS.128
+  const int srow = p0.Kp + 4;                                               // stash row stride (floats): conflict-free LDS/STS.128
   float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [128 pixels][Kp + 4] composed weights of one tile
   float* carry = stash + (size_t)srow * kTcTileM;                         // [128] front-range transmittance per pixel
   BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
@@ -278,8 +288,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
-  const uint32_t tmem_a = tmem + (uint32_t)p.c_tile;              // A hi; A lo follows at + Kp/kACols columns
-  const int a_cols = p.Kp / kACols;
+  const uint32_t tmem_a = tmem + (uint32_t)p0.c_tile;             // A hi; A lo follows at + Kp/kACols columns
+  const int a_cols = p0.Kp / kACols;
 
   int unit_it = 0;      // units processed by this CTA so far
   int tile_it = 0;      // tiles processed by this CTA so far (barrier phases)
@@ -289,18 +299,29 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   //   whole_runs  CTA i takes the whole runs i, i + gridDim.x, ... (large batches: fewest stagings, CTAs in lock-step)
   //   otherwise   the sequence is cut into gridDim.x contiguous, equally long ranges (+-1 tile), which a CTA walks as
   //               partial runs (small batches: balance matters more than the extra stagings)
-  const int g_end = p.whole_runs ? p.total_tiles : tc_range_begin(p.total_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
-  for (int g = p.whole_runs ? (int)blockIdx.x * p.tiles_per_image : tc_range_begin(p.total_tiles, (int)blockIdx.x, (int)gridDim.x);
-       g < g_end; ++unit_it) {
+  // Several levels (kP = -1): always equal ranges over the concatenated sequence.
+  const int seq_tiles = kP == -1 ? L.tile_start[L.n_levels] : p0.total_tiles;
+  const bool whole_runs = kP != -1 && p0.whole_runs;
+  const int g_end = whole_runs ? seq_tiles : tc_range_begin(seq_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
+  int level = 0;
+  for (int gs = whole_runs ? (int)blockIdx.x * p0.tiles_per_image : tc_range_begin(seq_tiles, (int)blockIdx.x, (int)gridDim.x);
+       gs < g_end; ++unit_it) {
+    if constexpr (kP == -1) {
+      while (gs >= L.tile_start[level + 1]) ++level;
+    }
+    const RenderTcParams& p = L.lv[kP == -1 ? level : 0];
+    const int g = gs - (kP == -1 ? L.tile_start[level] : 0);        // tile index within the level
     const int img_chunk = g / p.tiles_per_image;
     const int n = img_chunk / p.c_chunks;
     const int chunk = img_chunk - n * p.c_chunks;
     const int c0 = chunk * p.c_tile;
     const int t_lo = g - img_chunk * p.tiles_per_image;
-    const int ntiles = min(p.tiles_per_image - t_lo, g_end - g);
-    g += ntiles;
-    if (p.whole_runs) g += ((int)gridDim.x - 1) * p.tiles_per_image;
+    const int ntiles = min(p.tiles_per_image - t_lo, g_end - gs);
+    gs += ntiles;
+    if (whole_runs) gs += ((int)gridDim.x - 1) * p.tiles_per_image;
 
+    // plane stride: a compile-time constant for the single-level specialisations, per level at run time otherwise
+    const int P = kP > 0 ? kP : p.H * p.W;
     if (warp < kTcComputeWarps) {
       // =============================== stages 1+2 + operand staging ===============================
       // 8 warps: two per TMEM lane quarter.  Warp (half, q) owns pixels q*32..q*32+31 of the tile and one of
@@ -739,9 +760,12 @@ static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
     sm_dev = dev;
   }
   const int grid = std::min(sm_count, p.total_tiles);
-  RenderTcParams pq = p;
-  pq.pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
-  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(pq);
+  RenderTcLevels L{};
+  L.lv[0] = p;
+  L.lv[0].pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
+  L.n_levels = 1;
+  L.tile_start[1] = p.total_tiles;
+  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(L);
   BS_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,4 +17,59 @@ int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_
   return launch_tc_dtype<true>(p, pl.smem, dtype, st);
 }
 
+// Several stage-3 problems (pyramid levels) in one launch; L.lv[*] filled by fill_tc_units, equal Kp / c_tile / dtype.
+template <typename FT, typename OT, bool kTf32>
+static int launch_tc_levels_t(RenderTcLevels& L, size_t smem, cudaStream_t st) {
+  static thread_local int configured_dev = -1, sm_count = 0;
+  int dev = 0;
+  BS_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, 2, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    configured_dev = dev;
+  }
+  long long total = 0;
+  for (int i = 0; i < L.n_levels; ++i) {
+    L.tile_start[i] = (int)total;
+    total += L.lv[i].total_tiles;
+    L.lv[i].pair_ok = ((L.lv[i].H * L.lv[i].W) & 1) == 0 && (reinterpret_cast<uintptr_t>(L.lv[i].grid) & 7) == 0;
+  }
+  if (total > 0x7fffffffll) BS_UNSUPPORTED("too many tiles for one launch");
+  L.tile_start[L.n_levels] = (int)total;
+  if (total == 0) return 0;
+  const int grid = (int)std::min<long long>(sm_count, total);
+  render_tc_kernel<FT, OT, kTf32, 2, -1, true><<<grid, 13 * 32, smem, st>>>(L);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_tc_levels(RenderTcLevels& L, size_t smem, int dtype, cudaStream_t st) {
+  if (dtype == BLOBSPLAT_F32) return launch_tc_levels_t<float, float, true>(L, smem, st);
+  if (dtype == BLOBSPLAT_BF16) return launch_tc_levels_t<__nv_bfloat16, __nv_bfloat16, false>(L, smem, st);
+  if (dtype == BLOBSPLAT_F16) return launch_tc_levels_t<__half, __half, false>(L, smem, st);
+  BS_UNSUPPORTED("tensor-core engine: unsupported dtype %d", dtype);
+}
+
+// Up to kTcMaxLevels stage-3 problems of one pyramid (same N, K, dtype; per-level H, W, C) as ONE launch.  Returns
+// 1 (nothing launched) when the levels cannot share a launch — different channel tiles or operand depth — so the
+// caller runs them one by one.
+int feature_splat_levels_tc_dispatch(int n_levels, const void* const* scores, const int64_t* sn, const int64_t* sk,
+                                     const int64_t* sp, const void* const* feats, void* const* outs, int N, int K,
+                                     const int* C, const int* H, const int* W, int dtype, cudaStream_t st) {
+  if (n_levels < 2 || n_levels > kTcMaxLevels || dtype == BLOBSPLAT_F64) return 1;
+  RenderTcLevels L{};
+  TcPlan first{};
+  for (int i = 0; i < n_levels; ++i) {
+    const TcPlan pl = plan_tc(K, C[i], dtype == BLOBSPLAT_F32);
+    if (!pl.ok) return 1;
+    if (i == 0) first = pl;
+    else if (pl.Kp != first.Kp || pl.c_tile != first.c_tile || pl.smem != first.smem) return 1;
+    RenderTcParams& p = L.lv[i];
+    p.scores = scores[i]; p.sn = sn[i]; p.sk = sk[i]; p.sp = sp[i]; p.feats = feats[i]; p.grid = outs[i];
+    if (int rc = fill_tc_units(p, pl, N, K, H[i], W[i], C[i])) return rc;
+  }
+  L.n_levels = n_levels;
+  return launch_tc_levels(L, first.smem, dtype, st);
+}
+
 }  // namespace blobsplat

@@ -6,7 +6,7 @@ One function per C entry point (include/blobsplat.h).  The reference-signature l
 from __future__ import annotations
 
 import ctypes
-from typing import Dict, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -72,8 +72,8 @@ def render_scores(xs, ys, covs, sizes, height: int, width: int, select: str = "a
         return cat(0), cat(1)
     ksel = {"all": m + 1, "fg": m, "bg": 1}[select]
     dev = covs_c.device
-    composed = torch.empty((n, ksel, height, width), dtype=out_dtype, device=dev) if want_composed else None
-    raw = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=dev) if want_raw else None
+    composed = C.new_output((n, ksel, height, width), out_dtype, dev) if want_composed else None
+    raw = C.new_output((n, m + 1, height, width), out_dtype, dev) if want_raw else None
     oc = C.dtype_code(out_dtype)
     C.check(C.lib().blobsplat_scores(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.dtype_code(covs_c.dtype),
                                      n, m, height, width, _SELECT[select], C.ptr(composed), oc, C.ptr(raw), oc,
@@ -86,7 +86,7 @@ def composite(scores_nkhw: torch.Tensor) -> torch.Tensor:
     C.require_cuda(scores_nkhw, "scores")
     s = scores_nkhw.contiguous()
     n, k, h, w = s.shape
-    out = torch.empty_like(s)
+    out = C.new_output(s.shape, s.dtype, s.device)
     C.check(C.lib().blobsplat_composite(C.ptr(s), C.ptr(out), n, k, h, w, C.dtype_code(s.dtype), C.dev_of(s),
                                         C.stream_of(s)))
     return out
@@ -97,7 +97,7 @@ def resize_bilinear(img: torch.Tensor, out_h: int, out_w: int) -> torch.Tensor:
     C.require_cuda(img, "img")
     x = img.contiguous()
     n, c, h, w = x.shape
-    out = torch.empty((n, c, out_h, out_w), dtype=x.dtype, device=x.device)
+    out = C.new_output((n, c, out_h, out_w), x.dtype, x.device)
     C.check(C.lib().blobsplat_resize_bilinear(C.ptr(x), C.ptr(out), n * c, h, w, out_h, out_w, C.dtype_code(x.dtype),
                                               C.dev_of(x), C.stream_of(x)))
     return out
@@ -118,7 +118,7 @@ def halving_pyramid(img: torch.Tensor, cutoff: int) -> Dict[int, torch.Tensor]:
             todo += 1
         if todo:
             src = cur.contiguous()
-            outs = [torch.empty((n, c, w >> (l + 1), w >> (l + 1)), dtype=cur.dtype, device=cur.device)
+            outs = [C.new_output((n, c, w >> (l + 1), w >> (l + 1)), cur.dtype, cur.device)
                     for l in range(todo)]
             arr = (ctypes.c_void_p * todo)(*[o.data_ptr() for o in outs])
             C.check(C.lib().blobsplat_pyramid(C.ptr(src), arr, todo, n * c, w, C.dtype_code(cur.dtype),
@@ -166,10 +166,47 @@ def feature_splat(scores: torch.Tensor, features: torch.Tensor, channels_last: b
         strides = _linear_pixel_strides(s)
     sn, sk, sp = strides
     c = f.shape[2]
-    out = torch.empty((n, c, h, w), dtype=s.dtype, device=s.device)
+    out = C.new_output((n, c, h, w), s.dtype, s.device)
     C.check(C.lib().blobsplat_feature_splat(C.ptr(s), sn, sk, sp, C.ptr(f), C.ptr(out), n, k, c, h, w,
                                             C.dtype_code(s.dtype), _ENGINE[engine], C.dev_of(s), C.stream_of(s)))
     return out
+
+
+def feature_splat_levels(scores: Sequence[torch.Tensor], features: Sequence[torch.Tensor],
+                         engine: str = "auto") -> List[torch.Tensor]:
+    """Stage 3 for a whole pyramid (blobsplat_feature_splat_levels): scores[i] [N,K,H_i,W_i] x features[i] [N,K,C_i]
+    -> [N,C_i,H_i,W_i] for every level, as ONE tcgen05 launch when the levels share an operand tiling (BlobNet's
+    320/640/1280-channel levels do), level by level otherwise.  Same dtype / N / K on every level."""
+    if len(scores) != len(features):
+        raise RuntimeError("one feature tensor per score map")
+    if not scores:
+        return []
+    C.require_cuda(scores[0], "scores")
+    n, k = scores[0].shape[:2]
+    dt, dev = scores[0].dtype, scores[0].device
+    ss, fs, outs, strides, shapes = [], [], [], [], []
+    for s, f in zip(scores, features):
+        if s.ndim != 4 or f.ndim != 3 or s.shape[0] != n or s.shape[1] != k or s.dtype != dt or s.device != dev:
+            raise RuntimeError("levels must be [N,K,H,W] maps of one batch, dtype and device")
+        if f.shape[0] != n or f.shape[1] != k:
+            raise RuntimeError(f"einsum(): operands do not broadcast: scores {tuple(s.shape)} (N,K,H,W) vs features "
+                               f"{tuple(f.shape)} (N,K,C)")
+        st = _linear_pixel_strides(s)
+        if st is None:
+            s = s.contiguous()
+            st = _linear_pixel_strides(s)
+        f = f.to(dtype=dt, device=dev).contiguous()
+        ss.append(s); fs.append(f); strides.append(st); shapes.append((f.shape[2], s.shape[2], s.shape[3]))
+        outs.append(C.new_output((n, f.shape[2], s.shape[2], s.shape[3]), dt, dev))
+    L = len(ss)
+    ptrs = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    i64 = lambda vals: (ctypes.c_int64 * L)(*vals)
+    i32 = lambda vals: (ctypes.c_int * L)(*vals)
+    C.check(C.lib().blobsplat_feature_splat_levels(
+        L, ptrs(ss), i64([st[0] for st in strides]), i64([st[1] for st in strides]), i64([st[2] for st in strides]),
+        ptrs(fs), ptrs(outs), n, k, i32([sh[0] for sh in shapes]), i32([sh[1] for sh in shapes]),
+        i32([sh[2] for sh in shapes]), C.dtype_code(dt), _ENGINE[engine], C.dev_of(ss[0]), C.stream_of(ss[0])))
+    return outs
 
 
 def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width: int,
@@ -186,8 +223,8 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
         raise RuntimeError(f"features must be [N, M+1, C] = [{n}, {m + 1}, C], got {tuple(f.shape)}")
     c = f.shape[2]
     dev = covs_c.device
-    composed = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=dev) if want_composed else None
-    grid = torch.empty((n, c, height, width), dtype=out_dtype, device=dev)
+    composed = C.new_output((n, m + 1, height, width), out_dtype, dev) if want_composed else None
+    grid = C.new_output((n, c, height, width), out_dtype, dev)
     C.check(C.lib().blobsplat_render(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.ptr(f),
                                      C.dtype_code(f.dtype), n, m, height, width, c, C.ptr(composed), C.ptr(grid),
                                      C.dtype_code(out_dtype), C.dev_of(covs_c), C.stream_of(covs_c)))
@@ -228,8 +265,8 @@ def render_scores_from_ellipses(ellipses: torch.Tensor, sizes: Optional[torch.Te
         torch.as_tensor(sizes, device=e.device).to(torch.float32).reshape(n, m).contiguous()
     img_h, img_w = image_size
     ksel = {"all": m + 1, "fg": m, "bg": 1}[select]
-    composed = torch.empty((n, ksel, height, width), dtype=out_dtype, device=e.device)
-    raw = torch.empty((n, m + 1, height, width), dtype=out_dtype, device=e.device) if want_raw else None
+    composed = C.new_output((n, ksel, height, width), out_dtype, e.device)
+    raw = C.new_output((n, m + 1, height, width), out_dtype, e.device) if want_raw else None
     oc = C.dtype_code(out_dtype)
     C.check(C.lib().blobsplat_scores_ellipse(C.ptr(e), C.ptr(sz), float(img_w), float(img_h), n, m, height, width,
                                              _SELECT[select], C.ptr(composed), oc, C.ptr(raw), oc, C.dev_of(e),

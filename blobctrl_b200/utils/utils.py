@@ -238,9 +238,11 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
     if d is None:
         d, _ = ops.render_scores(xs, ys, covs, sizes, score_size, score_size, out_dtype=out_dtype)
     pyr = pyramid_resize(d, cutoff=min(level_features))
-    for s, f in level_features.items():
-        if s not in grids:
-            grids[s] = splat_features_from_scores(pyr[s], f.to(d.dtype), s, channels_last=False, engine=engine)
+    rest = [s for s in level_features if s not in grids]
+    # the remaining levels: one launch for the whole pyramid where the levels allow it (blobsplat_feature_splat_levels)
+    for s, g in zip(rest, ops.feature_splat_levels([pyr[s] for s in rest], [level_features[s].to(d.dtype) for s in rest],
+                                                   engine=engine)):
+        grids[s] = g
     return {"scores_pyramid": pyr, "feature_grids": grids}
 
 

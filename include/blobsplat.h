@@ -161,6 +161,21 @@ BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, 
                             int dtype, int engine, int device, void* stream);
 
 /*
+ * (3b) feature splat of a whole pyramid — the multi-resolution BlobNet conditioning (BASELINE configs[2]): the same
+ *      contraction as (3) for n_levels score maps of one batch (same N, K, dtype; per-level H, W, C), i.e. the loop
+ *      `for s in sizes: splat_features_from_scores(scores_pyramid[s], features[s], s)` over the pyramid returned by
+ *      splat_features (utils.py:235-241, 57-77).  All arrays are HOST arrays of n_levels entries (pointers are
+ *      device pointers).  engine AUTO / FMA: level by level exactly as (3).  engine TENSOR: when every level is
+ *      a dense contraction with the same operand tiling (2..4 levels, C[i] >= 64 and C[i] % 32 == 0 with one
+ *      common channel tile) the levels run as ONE tcgen05 launch over the concatenated tile sequence, otherwise
+ *      level by level on the tensor engine.
+ */
+BLOBSPLAT_API int blobsplat_feature_splat_levels(int n_levels, const void* const* scores, const int64_t* stride_n,
+                              const int64_t* stride_k, const int64_t* stride_p, const void* const* features,
+                              void* const* outs, int N, int K, const int* C, const int* H, const int* W, int dtype,
+                              int engine, int device, void* stream);
+
+/*
  * (3b) conditioning fill — fused construct_blobnet_input for the loop-invariant channels.
  *      Replaces the stage-3 splat at pipelines/pipeline_blobnet.py:984 plus the per-step torch.cat of
  *      construct_blobnet_input (:724-739, called at :1043-1049 and :1071-1076) for everything except the 4 latent

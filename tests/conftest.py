@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+os.environ.setdefault("BLOBSPLAT_POISON_OUTPUTS", "1")   # NaN-filled outputs: unwritten elements cannot pass by luck
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

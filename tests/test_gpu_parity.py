@@ -596,3 +596,35 @@ def test_fused_render_epilogue_paths(h, w, c, dtype, rel):
     ops.render_fused_into(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w, comp2, grid2)
     assert torch.equal(grid2, grid) and torch.equal(comp2, comp)
     assert float(store[0]) == 0.0
+
+
+@pytest.mark.parametrize("n,k,levels,dtype,rel", [
+    (3, 33, [(32, 32, 640), (16, 16, 1280), (8, 8, 1280)], torch.bfloat16, 1e-2),        # cfg3's lower levels
+    (2, 33, [(64, 64, 320), (32, 32, 640), (16, 16, 1280), (8, 8, 1280)], torch.float32, 1e-5),
+    (5, 17, [(12, 20, 320), (6, 10, 640), (3, 5, 320)], torch.float16, 2e-3),            # odd strides: generic path per unit
+    (1, 65, [(16, 16, 640), (8, 8, 320)], torch.float32, 1e-5),
+    (2, 33, [(16, 16, 96), (8, 8, 320)], torch.float32, 1e-5),                           # different channel tiles: level by level
+    (2, 5, [(16, 16, 64), (8, 8, 3)], torch.float32, 1e-5)])                             # tiny K / C: FMA engine per level
+def test_feature_splat_levels_vs_oracle(n, k, levels, dtype, rel):
+    """blobsplat_feature_splat_levels: a pyramid of stage-3 problems (one launch when the levels share a tiling) against
+    the float64 oracle per level, and bit-identical to the single-level entry point."""
+    from blobctrl_b200 import ops
+    g = torch.Generator().manual_seed(n * 131 + k)
+    scs, fts = [], []
+    for (h, w, c) in levels:
+        sc = torch.rand(n, k, h, w, generator=g)
+        scs.append((sc / sc.sum(1, keepdim=True)).to(DEV).to(dtype))
+        fts.append(torch.randn(n, k, c, generator=g).to(DEV).to(dtype))
+    outs = ops.feature_splat_levels(scs, fts)
+    assert len(outs) == len(levels)
+    if k >= 12 and all(c % 32 == 0 and c >= 64 for _, _, c in levels):
+        fused = ops.feature_splat_levels(scs, fts, engine="tensor")      # the single-launch path
+        for a, b in zip(fused, outs):
+            assert torch.equal(a, b), "single-launch pyramid differs from the per-level launches"
+    for (h, w, c), sc, ft, out in zip(levels, scs, fts, outs):
+        assert out.shape == (n, c, h, w) and out.dtype == dtype and out.is_contiguous()
+        want = blob_oracle.splat_features_from_scores(_np(sc).astype(np.float64), _np(ft).astype(np.float64), None,
+                                                      channels_last=False)
+        close_scaled(_np(out), want, rel, f"level {h}x{w} C={c}")
+        assert torch.equal(out, ops.feature_splat(sc, ft)), f"level {h}x{w}: differs from the single-level call"
+    assert ops.feature_splat_levels([], []) == []
