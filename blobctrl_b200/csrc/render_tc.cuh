@@ -19,14 +19,16 @@
 // bar, at 1/3 of TF32 rate which still leaves the tensor pipe at ~50% of the HBM-bound tile time.
 // bf16/f16 maps use one kind::f16 MMA per k-step.
 //
-// Warp roles (416 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
+// Warp roles (512 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
 //   warps 0-7   stages 1+2 for one 128-pixel tile, two warps per TMEM lane quarter: each composites one
 //               of two blob ranges (a two-level multiplicative suffix scan across blobs, carry through
 //               shared memory), d_k -> global composed planes (coalesced) and a shared-memory stash;
-//               then, once the MMA has released A, stash -> hi/lo -> tcgen05.st.  Also stage the unit's
-//               features (B) and blob coefficients.
+//               then, once the MMA has released A, stash -> hi/lo -> tcgen05.st.  Also compute the unit's
+//               blob coefficients, and stage its features (B) when shared memory holds only one B buffer.
 //   warps 8-11  epilogue: tcgen05.ld D half -> registers -> coalesced global stores of [N,C,H,W].
 //   warp  12    TMEM allocation + single-thread tcgen05.mma issue + tcgen05.commit to mbarriers.
+//   warps 13-15 operand staging: when several B buffers fit (16-bit maps, small K) they fill a ring of up to 4
+//               ahead of the units, so a unit's features are in place before its first tile reaches the MMA.
 #pragma once
 #include <cstdlib>
 
@@ -49,6 +51,12 @@
 #ifndef BS_STAGE_COST
 #define BS_STAGE_COST 3        // cost of staging one unit's operands, in tiles (loads queue behind the saturated store stream)
 #endif
+#ifndef BS_RING_MIN_UNITS
+#define BS_RING_MIN_UNITS 3   // use the B ring when a CTA processes at least this many units
+#endif
+#ifndef BS_MAX_B
+#define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
+#endif
 #ifndef BS_RNA_CUSTOM
 #define BS_RNA_CUSTOM 1
 #endif
@@ -63,6 +71,9 @@ constexpr int kTcMaxCTile = 320;
 // offset 3 every group of 8 blobs of a range that ends on a multiple of 8 occupies two 16-byte aligned float4s of the
 // pixel-major stash, so stage 1/2, the rescale pass and the TMEM conversion all use 128-bit shared-memory accesses.
 constexpr int kTcKOff = 3;
+constexpr int kTcMaxB = 4;                       // ring of B operand buffers (when they fit)
+constexpr int kTcStageWarps = 3;                 // staging warps: with the 13 others a CTA is 16 warps (registers are
+                                                 // allocated for warp counts rounded up to 4 anyway)
 constexpr int kTcMaxBlobs = 127;                 // coefficient table: 127 * 32 B
 constexpr size_t kTcSmemBudget = 227 * 1024 - 256;
 
@@ -218,6 +229,8 @@ struct RenderTcParams {
   int K, Kp;              // K = M + 1; Kp = K rounded up to the MMA k-step (8 tf32 / 16 f16)
   int c_tile, c_chunks;   // channels per work unit (multiple of 32, <= 320); ceil(C / c_tile)
   int tiles_per_image;    // 128-pixel tiles per image
+  int nb;                 // B operand buffers in shared memory (ring); > 1: the staging warps run ahead of the units
+  int smem_bytes;         // dynamic shared memory of the launch (fixed part + nb B slots)
   int whole_runs;         // schedule: whole (image, chunk) runs round-robin vs contiguous equal tile ranges
   int total_tiles;        // N * c_chunks * tiles_per_image, linear index ((n * c_chunks + chunk) * tiles_per_image + tile)
   int pair_ok;            // float maps: grid planes allow aligned 2-pixel stores (P even, base 8-byte aligned)
@@ -238,9 +251,62 @@ struct RenderTcLevels {
 };
 
 struct TcBarriers {
-  uint64_t a_full, a_free, b_full, b_free, d_full[2], d_empty[2];
+  uint64_t a_full, a_free, b_full[kTcMaxB], b_free[kTcMaxB], d_full[2], d_empty[2];
   uint32_t tmem_base;
 };
+
+// Stage one unit's B operand: features [K, C] (c contiguous) of image n, channels c0 .. c0 + c_tile - 1, into the K-major
+// no-swizzle operand layout at b_dst (second copy = TF32 residuals at + b_bytes).  Called by `nthreads` threads.
+template <typename FT, typename OT, bool kTf32>
+__device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c0, unsigned char* b_smem, size_t b_bytes,
+                                           int tid, int nthreads) {
+  using BT = typename std::conditional<kTf32, float, OT>::type;
+  // features [K, C] (c contiguous) -> K-major operand rows: item (kc, c) = the T k-values kc*T .. kc*T+T-1 of
+  // channel c as one 16-byte chunk.  One thread moves a T x VC block: T 128-bit global loads (VC adjacent
+  // channels of one feature row each, coalesced across the warp), transposed in registers into VC items.
+  const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
+  constexpr int T = (16 / (int)sizeof(BT));
+  constexpr int VC = 16 / sizeof(FT);
+  const int cq = p.c_tile / VC;
+  const int blocks = (p.Kp / T) * cq;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C % VC) == 0;
+  for (int qi = tid; qi < blocks; qi += nthreads) {
+    const int kc = qi / cq, c = (qi - kc * cq) * VC;
+    const int ch = c0 + c;
+    float v[T][VC];
+#pragma unroll
+    for (int j = 0; j < T; ++j) {
+      const int k = kc * T + j - kTcKOff;                          // operand row k' = k + kTcKOff
+      const bool ok = k >= 0 && k < p.K && ch < p.C;
+      if (ok && vec_ok) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(f + (size_t)k * p.C + ch));
+        const FT* e = reinterpret_cast<const FT*>(&raw);
+#pragma unroll
+        for (int cc = 0; cc < VC; ++cc) v[j][cc] = (float)Cvt<FT>::to(e[cc]);
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < VC; ++cc)
+          v[j][cc] = (ok && ch + cc < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch + cc)) : 0.0f;
+      }
+    }
+    unsigned char* dst = b_smem + ((size_t)kc * p.c_tile + c) * 16;
+#pragma unroll
+    for (int cc = 0; cc < VC; ++cc) {
+      if constexpr (kTf32) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j][cc]); lo[j] = rna_tf32(v[j][cc] - hi[j]); }
+        *reinterpret_cast<float4*>(dst + cc * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(dst + cc * 16 + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      } else {
+        OT h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[j][cc]);
+        *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h);
+      }
+    }
+  }
+}
 
 // FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
 // kP: pixels per image when it is one of the common sizes (64^2, 32^2, 16^2), else 0 = runtime.  With a
@@ -248,8 +314,10 @@ struct TcBarriers {
 // kP = -1: several pyramid levels in one launch (RenderTcLevels); every work unit reads its own level's shape.
 // kFromScores: the A operand comes from precomputed score maps in global memory (stand-alone stage 3,
 // splat_features_from_scores) instead of being rendered from blob parameters (stages 1+2).
-template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
-__global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(const __grid_constant__ RenderTcLevels L) {
+// kRing: the CTA has the 3 staging warps and a ring of p.nb >= 2 B buffers; otherwise one buffer, staged by the compute
+// warps between units (the float path at BlobNet's sizes, where B fills shared memory, and launches with few units).
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores, bool kRing>
+__global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32, 1) render_tc_kernel(const __grid_constant__ RenderTcLevels L) {
   const RenderTcParams& p0 = L.lv[0];     // Kp, c_tile and the dtypes are the same for every level
   constexpr int kTcComputeWarps = 4 * kHalves;
   constexpr int kTcComputeThreads = kTcComputeWarps * 32;
@@ -263,9 +331,11 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
 
   const int c_half = p0.c_tile >> 1;
   const size_t b_bytes = (size_t)(p0.Kp / kElemsPer16B) * p0.c_tile * 16;   // one B copy
-  unsigned char* b_smem = smem;                                            // [kNumB][Kp/T][c_tile][16 B]
+  unsigned char* b_smem = smem;                                            // [nb][kNumB][Kp/T][c_tile][16 B]
+  const int nb = kRing ? p0.nb : 1;
+  const size_t b_stride = kNumB * b_bytes;                                 // one ring slot
   const int srow = p0.Kp + 4;                                               // stash row stride (floats): conflict-free LDS/STS.128
-  float* stash = reinterpret_cast<float*>(smem + kNumB * b_bytes);         // [128 pixels][Kp + 4] composed weights of one tile
+  float* stash = reinterpret_cast<float*>(smem + nb * b_stride);         // [128 pixels][Kp + 4] composed weights of one tile
   float* carry = stash + (size_t)srow * kTcTileM;                         // [128] front-range transmittance per pixel
   BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
@@ -275,7 +345,9 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
   if (warp == kTcMmaWarp) {
     if (lane == 0) {
       mbar_init(&bars->a_full, kTcComputeThreads); mbar_init(&bars->a_free, 1);
-      mbar_init(&bars->b_full, kTcComputeThreads); mbar_init(&bars->b_free, 1);
+      for (int i = 0; i < kTcMaxB; ++i) {   // B is staged by the staging warps when there is a ring, else by the compute warps
+        mbar_init(&bars->b_full[i], kRing ? kTcStageWarps * 32 : kTcComputeThreads); mbar_init(&bars->b_free[i], 1);
+      }
       mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
       mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -347,56 +419,12 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
       if (unit_it == 0) {   // stash columns that are never written (k' < kTcKOff, k' >= K + kTcKOff) stay zero for the whole kernel
         for (int i = ctid; i < kTcTileM * srow; i += kTcComputeThreads) stash[i] = 0.0f;
       }
-      if (unit_it > 0) mbar_wait(&bars->b_free, (unit_it - 1) & 1);   // MMAs of the previous unit have read B
-      {
-        // features [K, C] (c contiguous) -> K-major operand rows: item (kc, c) = the T k-values kc*T .. kc*T+T-1 of
-        // channel c as one 16-byte chunk.  One thread moves a T x VC block: T 128-bit global loads (VC adjacent
-        // channels of one feature row each, coalesced across the warp), transposed in registers into VC items.
-        const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
-        constexpr int T = kElemsPer16B;
-        constexpr int VC = 16 / sizeof(FT);
-        const int cq = p.c_tile / VC;
-        const int blocks = (p.Kp / T) * cq;
-        const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C % VC) == 0;
-        for (int qi = ctid; qi < blocks; qi += kTcComputeThreads) {
-          const int kc = qi / cq, c = (qi - kc * cq) * VC;
-          const int ch = c0 + c;
-          float v[T][VC];
-#pragma unroll
-          for (int j = 0; j < T; ++j) {
-            const int k = kc * T + j - kTcKOff;                          // operand row k' = k + kTcKOff
-            const bool ok = k >= 0 && k < p.K && ch < p.C;
-            if (ok && vec_ok) {
-              const uint4 raw = __ldg(reinterpret_cast<const uint4*>(f + (size_t)k * p.C + ch));
-              const FT* e = reinterpret_cast<const FT*>(&raw);
-#pragma unroll
-              for (int cc = 0; cc < VC; ++cc) v[j][cc] = (float)Cvt<FT>::to(e[cc]);
-            } else {
-#pragma unroll
-              for (int cc = 0; cc < VC; ++cc)
-                v[j][cc] = (ok && ch + cc < p.C) ? (float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + ch + cc)) : 0.0f;
-            }
-          }
-          unsigned char* dst = b_smem + ((size_t)kc * p.c_tile + c) * 16;
-#pragma unroll
-          for (int cc = 0; cc < VC; ++cc) {
-            if constexpr (kTf32) {
-              float hi[4], lo[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j][cc]); lo[j] = rna_tf32(v[j][cc] - hi[j]); }
-              *reinterpret_cast<float4*>(dst + cc * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<float4*>(dst + cc * 16 + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            } else {
-              OT h[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) h[j] = Cvt<OT>::from(v[j][cc]);
-              *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h);
-            }
-          }
-        }
+      if constexpr (!kRing) {   // single B buffer: staged here, after the MMAs of the previous unit have read it
+        if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
+        tc_stage_b<FT, OT, kTf32>(p, n, c0, b_smem, b_bytes, ctid, kTcComputeThreads);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
+        mbar_arrive(&bars->b_full[0]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
-      mbar_arrive(&bars->b_full);
       uint32_t any_general;   // barrier + OR-reduce: coef visible to all compute threads; does any blob need the slow form?
       asm volatile(
           "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
@@ -640,13 +668,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           mbar_arrive(&bars->d_empty[h]);
         }
       }
-    } else {
+    } else if (warp == kTcMmaWarp) {
       // ========================================= MMA issue =========================================
       if (lane == 0) {
+        const int buf = unit_it % nb, rnd = unit_it / nb;      // this unit's slot of the B ring
         const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<OT, __half>::value ? 0u : 1u), (uint32_t)c_half);
-        const uint32_t b_base = smem_u32(b_smem);
+        const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_stride);
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
-        mbar_wait(&bars->b_full, unit_it & 1);
+        mbar_wait(&bars->b_full[buf], rnd & 1);
         for (int t = 0; t < ntiles; ++t, ++tile_it) {
           mbar_wait(&bars->a_full, tile_it & 1);
           tc_fence_after();
@@ -672,16 +701,26 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
           }
           tc_commit(&bars->a_free);
         }
-        tc_commit(&bars->b_free);
+        tc_commit(&bars->b_free[buf]);
       }
       __syncwarp();
+    } else if constexpr (kRing) {
+      // ====================================== operand staging ======================================
+      // 3 warps that run ahead of the units: B of unit u goes into ring slot u % nb as soon as the MMAs of unit u - nb
+      // have released it, so staging overlaps the tiles of the units before it
+      const int buf = unit_it % nb, rnd = unit_it / nb;
+      if (rnd > 0) mbar_wait(&bars->b_free[buf], (rnd - 1) & 1);
+      tc_stage_b<FT, OT, kTf32>(p, n, c0, b_smem + (size_t)buf * b_stride, b_bytes, (int)threadIdx.x - (kTcMmaWarp + 1) * 32,
+                                kTcStageWarps * 32);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
+      mbar_arrive(&bars->b_full[buf]);
     }
   }
 
   // the last commits arrive asynchronously: see them land before the CTA (and its smem barriers) goes away
   if (warp == kTcMmaWarp && lane == 0 && tile_it > 0) {
     mbar_wait(&bars->a_free, (tile_it - 1) & 1);
-    mbar_wait(&bars->b_free, (unit_it - 1) & 1);
+    mbar_wait(&bars->b_free[(unit_it - 1) % nb], ((unit_it - 1) / nb) & 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -694,7 +733,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5) * 32, 1) render_tc_kernel(co
 // ---- host side ---------------------------------------------------------------------------------------
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct TcPlan { int Kp, c_tile; size_t smem; bool ok; const char* why; };
+struct TcPlan { int Kp, c_tile, nb; size_t smem, b_slot; bool ok; const char* why; };   // smem = fixed part + nb * b_slot
 
 static inline TcPlan plan_tc(int K, int C, bool tf32) {
   TcPlan pl{};
@@ -714,7 +753,10 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
   for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
     if (C % c == 0) { c_tile = c; break; }
   pl.c_tile = c_tile;
-  pl.smem = fixed + per_c * c_tile;
+  // as many B buffers as fit (ring, staged ahead by the staging warps); one when B fills shared memory
+  pl.nb = (int)std::min<size_t>(BS_MAX_B, (kTcSmemBudget - fixed) / (per_c * c_tile));
+  pl.b_slot = per_c * c_tile;
+  pl.smem = fixed + (size_t)pl.nb * pl.b_slot;
   pl.ok = true;
   return pl;
 }
@@ -733,25 +775,33 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = std::min(sms, p.total_tiles);
   long long ranges = 0;                                        // worst CTA under equal tile ranges
+  int range_units = 0;
   for (int i = 0; i < ctas; ++i) {
     const int lo = tc_range_begin(p.total_tiles, i, ctas), hi = tc_range_begin(p.total_tiles, i + 1, ctas);
     if (hi <= lo) continue;
     const int units = (hi - 1) / p.tiles_per_image - lo / p.tiles_per_image + 1;
+    range_units = std::max(range_units, units);
     ranges = std::max<long long>(ranges, (hi - lo) + 2ll * BS_STAGE_COST * units);   // staggered stagings queue behind other CTAs' stores: twice the cost
   }
   const long long runs = total / p.tiles_per_image;
-  const long long whole = ctas > 0 ? (runs + ctas - 1) / ctas * (p.tiles_per_image + BS_STAGE_COST) : 0;
+  const long long whole_units = ctas > 0 ? (runs + ctas - 1) / ctas : 0;
+  const long long whole = whole_units * (p.tiles_per_image + BS_STAGE_COST);
   p.whole_runs = whole <= ranges ? 1 : 0;
+  // B ring + staging warps only where a CTA has enough units for staging to run ahead of; with one or two units per
+  // CTA the 256 compute threads stage faster than the 96 staging threads and there is nothing to overlap with
+  const long long units_per_cta = p.whole_runs ? whole_units : range_units;
+  p.nb = (pl.nb >= 2 && units_per_cta >= BS_RING_MIN_UNITS) ? pl.nb : 1;
+  p.smem_bytes = (int)(pl.smem - (size_t)(pl.nb - p.nb) * pl.b_slot);
   return 0;
 }
 
-template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
-static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores, bool kRing>
+static int launch_tc_pr(const RenderTcParams& p, cudaStream_t st) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
   static thread_local int sm_count = 0, sm_dev = -1;
@@ -765,9 +815,18 @@ static int launch_tc_p(const RenderTcParams& p, size_t smem, cudaStream_t st) {
   L.lv[0].pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
   L.n_levels = 1;
   L.tile_start[1] = p.total_tiles;
-  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores><<<grid, (4 * kHalves + 5) * 32, smem, st>>>(L);
+  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>
+      <<<grid, (4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32, (size_t)p.smem_bytes, st>>>(L);
   BS_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
+static int launch_tc_p(const RenderTcParams& p, size_t, cudaStream_t st) {
+  if constexpr (kHalves == 2) {
+    if (p.nb > 1) return launch_tc_pr<FT, OT, kTf32, kHalves, kP, kFromScores, true>(p, st);
+  }
+  return launch_tc_pr<FT, OT, kTf32, kHalves, kP, kFromScores, false>(p, st);
 }
 
 template <typename FT, typename OT, bool kTf32, int kHalves, bool kFromScores>

@@ -18,13 +18,13 @@ int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_
 }
 
 // Several stage-3 problems (pyramid levels) in one launch; L.lv[*] filled by fill_tc_units, equal Kp / c_tile / dtype.
-template <typename FT, typename OT, bool kTf32>
-static int launch_tc_levels_t(RenderTcLevels& L, size_t smem, cudaStream_t st) {
+template <typename FT, typename OT, bool kTf32, bool kRing>
+static int launch_tc_levels_r(RenderTcLevels& L, size_t smem, cudaStream_t st) {
   static thread_local int configured_dev = -1, sm_count = 0;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, 2, -1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured_dev = dev;
   }
@@ -38,9 +38,15 @@ static int launch_tc_levels_t(RenderTcLevels& L, size_t smem, cudaStream_t st) {
   L.tile_start[L.n_levels] = (int)total;
   if (total == 0) return 0;
   const int grid = (int)std::min<long long>(sm_count, total);
-  render_tc_kernel<FT, OT, kTf32, 2, -1, true><<<grid, 13 * 32, smem, st>>>(L);
+  render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing><<<grid, (13 + (kRing ? kTcStageWarps : 0)) * 32, smem, st>>>(L);
   BS_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <typename FT, typename OT, bool kTf32>
+static int launch_tc_levels_t(RenderTcLevels& L, size_t smem, cudaStream_t st) {
+  return L.lv[0].nb > 1 ? launch_tc_levels_r<FT, OT, kTf32, true>(L, smem, st)
+                        : launch_tc_levels_r<FT, OT, kTf32, false>(L, smem, st);
 }
 
 static int launch_tc_levels(RenderTcLevels& L, size_t smem, int dtype, cudaStream_t st) {
@@ -69,6 +75,8 @@ int feature_splat_levels_tc_dispatch(int n_levels, const void* const* scores, co
     if (int rc = fill_tc_units(p, pl, N, K, H[i], W[i], C[i])) return rc;
   }
   L.n_levels = n_levels;
+  // a pyramid launch has many short units per CTA: always use the B ring when more than one buffer fits
+  for (int i = 0; i < n_levels; ++i) L.lv[i].nb = first.nb;
   return launch_tc_levels(L, first.smem, dtype, st);
 }
 

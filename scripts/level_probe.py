@@ -30,3 +30,12 @@ for n in (64, 8, 1):
             except Exception as e:
                 row.append(f"{eng} failed: {str(e)[:40]}")
         print(" ".join(row))
+
+# the three lower cfg3 levels: per-level launches (engine auto) vs ONE launch (engine tensor)
+n = 64
+scs, fts = [], []
+for s, c in ((32, 640), (16, 1280), (8, 1280)):
+    sc = torch.rand(n, 33, s, s, device="cuda"); scs.append((sc / sc.sum(1, keepdim=True)).to(torch.bfloat16))
+    fts.append(torch.randn(n, 33, c, device="cuda").to(torch.bfloat16))
+for eng in ("auto", "tensor"):
+    print(f"cfg3 levels 32/16/8 engine={eng}: {timed(lambda: ops.feature_splat_levels(scs, fts, engine=eng)):.1f} us")
