@@ -236,7 +236,7 @@ def main():
         out_host = torch.empty((M_BLOBS + 1 + CHANNELS, SIZE, SIZE), dtype=torch.float32).pin_memory()
 
         from blobctrl_b200.streaming import HostRenderer
-        host_renderer = HostRenderer(N_IMG, M_BLOBS, SIZE, CHANNELS, torch.float32, dev, chunks=8)
+        host_renderer = HostRenderer(N_IMG, M_BLOBS, SIZE, CHANNELS, torch.float32, dev, chunks=4)
 
         def e2e_step():
             # public host-input API: chunked H2D on a copy stream overlapped with the fused render

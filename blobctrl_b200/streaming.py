@@ -21,45 +21,53 @@ class HostRenderer:
     events, so steady-state calls allocate nothing."""
 
     def __init__(self, n: int, m: int, size: int, channels: int, dtype: torch.dtype = torch.float32,
-                 device="cuda", chunks: int = 8):
+                 device="cuda", chunks: int = 4, input_sets: int = 2):
         self.n, self.m, self.size, self.c, self.dtype = n, m, size, channels, dtype
         self.device = torch.device(device)
         self.bounds = [(i * n // chunks, (i + 1) * n // chunks) for i in range(chunks) if (i + 1) * n // chunks > i * n // chunks]
         dev = self.device
-        self.xs = torch.empty((n, m), dtype=torch.float32, device=dev)
-        self.ys = torch.empty_like(self.xs)
-        self.sizes = torch.empty_like(self.xs)
-        self.covs = torch.empty((n, m, 2, 2), dtype=torch.float32, device=dev)
-        self.feats = torch.empty((n, m + 1, channels), dtype=dtype, device=dev)
+        # input staging is double-buffered: the copies of call i+1 start while the last chunks of call i still render
+        self.sets = []
+        for _ in range(max(1, input_sets)):
+            st = {"xs": torch.empty((n, m), dtype=torch.float32, device=dev),
+                  "ys": torch.empty((n, m), dtype=torch.float32, device=dev),
+                  "sizes": torch.empty((n, m), dtype=torch.float32, device=dev),
+                  "covs": torch.empty((n, m, 2, 2), dtype=torch.float32, device=dev),
+                  "feats": torch.empty((n, m + 1, channels), dtype=dtype, device=dev),
+                  "done": torch.cuda.Event()}          # renders that read this set have been enqueued / finished
+            self.sets.append(st)
+        self.turn = 0
         self.composed = torch.empty((n, m + 1, size, size), dtype=dtype, device=dev)
         self.grid = torch.empty((n, channels, size, size), dtype=dtype, device=dev)
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.ready = [torch.cuda.Event() for _ in self.bounds]
-        self.done = torch.cuda.Event()
 
     def __call__(self, xs, ys, covs, sizes, features) -> Dict[str, torch.Tensor]:
         """xs, ys, sizes [N,M], covs [N,M,2,2], features [N,M+1,C]: HOST tensors (pinned for async copies).
-        Returns {'scores_pyramid': {S: composed}, 'feature_grid': grid} on the device (views of owned buffers)."""
+        Returns {'scores_pyramid': {S: composed}, 'feature_grid': grid} on the device (views of owned buffers,
+        overwritten by the next call — stream-ordered after anything already enqueued on the current stream)."""
         main = torch.cuda.current_stream(self.device)
-        self.copy_stream.wait_event(self.done)          # previous call's renders have consumed the staging buffers
+        st = self.sets[self.turn]
+        self.turn = (self.turn + 1) % len(self.sets)
+        self.copy_stream.wait_event(st["done"])         # the renders of the call that last used this set have read it
         with torch.cuda.stream(self.copy_stream):
             for i, (lo, hi) in enumerate(self.bounds):
-                self.xs[lo:hi].copy_(xs[lo:hi], non_blocking=True)
-                self.ys[lo:hi].copy_(ys[lo:hi], non_blocking=True)
-                self.sizes[lo:hi].copy_(sizes[lo:hi], non_blocking=True)
-                self.covs[lo:hi].copy_(covs[lo:hi], non_blocking=True)
-                self.feats[lo:hi].copy_(features[lo:hi], non_blocking=True)
+                st["xs"][lo:hi].copy_(xs[lo:hi], non_blocking=True)
+                st["ys"][lo:hi].copy_(ys[lo:hi], non_blocking=True)
+                st["sizes"][lo:hi].copy_(sizes[lo:hi], non_blocking=True)
+                st["covs"][lo:hi].copy_(covs[lo:hi], non_blocking=True)
+                st["feats"][lo:hi].copy_(features[lo:hi], non_blocking=True)
                 self.ready[i].record(self.copy_stream)
         for i, (lo, hi) in enumerate(self.bounds):
             main.wait_event(self.ready[i])
-            ops.render_fused_into(self.xs[lo:hi], self.ys[lo:hi], self.covs[lo:hi], self.sizes[lo:hi], self.feats[lo:hi],
+            ops.render_fused_into(st["xs"][lo:hi], st["ys"][lo:hi], st["covs"][lo:hi], st["sizes"][lo:hi], st["feats"][lo:hi],
                                   self.size, self.size, self.composed[lo:hi], self.grid[lo:hi])
-        self.done.record(main)
+        st["done"].record(main)
         return {"scores_pyramid": {self.size: self.composed}, "feature_grid": self.grid}
 
 
 def render_from_host(xs, ys, covs, sizes, features, score_size: int, dtype: Optional[torch.dtype] = None,
-                     device="cuda", chunks: int = 8, _cache={}) -> Dict[str, torch.Tensor]:
+                     device="cuda", chunks: int = 4, _cache={}) -> Dict[str, torch.Tensor]:
     """One-shot convenience wrapper: keeps one HostRenderer per shape."""
     n, m = covs.shape[:2]
     dtype = dtype or features.dtype
