@@ -263,7 +263,7 @@ def main():
             "unit": "GB/s", "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the
             # ncu --set full capture summarised in profiles/render_tc_r1.md (0.0872 GB read + 6.4000 GB written)
-            "traffic": 6487169744 if dom["name"].startswith("render_tc") else None,
+            "traffic": 6486408992 if dom["name"].startswith("render_tc") else None,
             "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["ms"],
             "step_alg_bytes": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4),
             "step_frac": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4) / (total / args.steps) / 1e9 / peak,
