@@ -249,7 +249,8 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
   BS_CHECK_ARG((long long)H * W < (1ll << 31), "H*W must fit in int32");
   BS_CHECK_ARG(valid_dtype(feat_dtype) && valid_dtype(out_dtype), "bad dtype");
   if (N == 0) return BLOBSPLAT_OK;
-  BS_CHECK_ARG(xs && ys && covs && sizes && features && grid, "NULL pointer");
+  BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");   // no blobs: background only
+  BS_CHECK_ARG(features && grid, "NULL pointer");
   const char* why = nullptr;
   if (!render_tc_supported(M + 1, C, H, W, feat_dtype, out_dtype, &why)) BS_UNSUPPORTED("fused render: %s", why);
   DeviceGuard g(device);

@@ -628,3 +628,40 @@ def test_feature_splat_levels_vs_oracle(n, k, levels, dtype, rel):
         close_scaled(_np(out), want, rel, f"level {h}x{w} C={c}")
         assert torch.equal(out, ops.feature_splat(sc, ft)), f"level {h}x{w}: differs from the single-level call"
     assert ops.feature_splat_levels([], []) == []
+
+
+@pytest.mark.parametrize("n,m,h,w,c,dtype,rel", [
+    (500, 12, 16, 16, 64, torch.bfloat16, 1e-2),     # 4 whole runs per CTA, 4 B buffers: staging warps + ring
+    (700, 20, 16, 24, 96, torch.float16, 2e-3),      # 5 runs per CTA, 3 tiles each
+    (460, 9, 16, 16, 64, torch.float32, 1e-5),       # float maps with a small B: the ring kernel in 3xTF32
+    (300, 40, 20, 20, 320, torch.bfloat16, 1e-2),    # partial last tile (400 px), 320 channels
+    (150, 12, 32, 32, 64, torch.bfloat16, 1e-2),     # 1-2 runs per CTA: single-buffer kernel for comparison
+    (37, 127, 12, 12, 32, torch.float32, 1e-5),      # the blob limit of the fused kernel
+    (5, 0, 9, 9, 32, torch.float32, 1e-5)])          # background only
+def test_fused_render_schedules_and_staging_ring(n, m, h, w, c, dtype, rel):
+    """blobsplat_render across its schedules (whole runs / equal ranges) and both staging schemes (compute warps with one
+    B buffer / staging warps with a ring), every image against the float64 oracle."""
+    from blobctrl_b200 import ops
+    if m == 0:   # no blobs: the background takes every pixel (alpha 1, nothing in front)
+        rng = np.random.default_rng(7)
+        syn = {"xs": np.zeros((n, 0), np.float32), "ys": np.zeros((n, 0), np.float32), "sizes": np.zeros((n, 0), np.float32),
+               "covs": np.zeros((n, 0, 2, 2), np.float32), "features": rng.standard_normal((n, 1, c)).astype(np.float32)}
+        want_d = np.ones((n, 1, h, w))
+    else:
+        syn = blob_oracle.synthetic_blobs(n, m, seed=n + m, c=c)
+        raw = blob_oracle.raw_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], h, w, np.float64)
+        _, dref = blob_oracle.composite(raw)
+        want_d = np.moveaxis(dref, -1, 1)
+    b = _blob(syn)
+    feats = _cuda(syn["features"]).to(dtype)
+    want_g = blob_oracle.splat_features_from_scores(want_d, _np(feats).astype(np.float64), None, channels_last=False)
+    comp, grid = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w)
+    close_scaled(_np(comp), want_d, rel, f"composed N={n} M={m}")
+    if m == 0:
+        return
+    close_scaled(_np(grid), want_g, 2 * rel, f"grid N={n} M={m} C={c}")
+    # the stand-alone stage 3 on the same weights takes the other A source through the same schedules
+    g2 = ops.feature_splat(comp, feats, engine="tensor")
+    want_g2 = blob_oracle.splat_features_from_scores(_np(comp).astype(np.float64), _np(feats).astype(np.float64), None,
+                                                     channels_last=False)
+    close_scaled(_np(g2), want_g2, 2 * rel, f"stage 3 from maps N={n} M={m} C={c}")
