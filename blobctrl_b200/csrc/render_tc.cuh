@@ -54,6 +54,9 @@
 #ifndef BS_RING_MIN_UNITS
 #define BS_RING_MIN_UNITS 3   // use the B ring when a CTA processes at least this many units
 #endif
+#ifndef BS_B_NMAJOR
+#define BS_B_NMAJOR 1         // 16-bit maps: N-major B operand (raw 16-byte copies) instead of K-major (transposed)
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
@@ -181,9 +184,11 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
          ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10, K-major both, N>>3 @17, M>>4 @24
-__device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t n) {
-  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((n >> 3) << 17) | ((uint32_t)(kTcTileM >> 4) << 24);
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10, A K-major, b_major @16 (1 = N-major), N>>3 @17,
+// M>>4 @24
+__device__ __forceinline__ uint32_t make_idesc(uint32_t ab_format, uint32_t n, uint32_t b_n_major) {
+  return (1u << 4) | (ab_format << 7) | (ab_format << 10) | (b_n_major << 16) | ((n >> 3) << 17) |
+         ((uint32_t)(kTcTileM >> 4) << 24);
 }
 
 // Round-to-nearest (ties away) to TF32's 10 explicit mantissa bits: (bits + 0x1000) & ~0x1fff.  Same result as
@@ -261,6 +266,44 @@ template <typename FT, typename OT, bool kTf32>
 __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c0, unsigned char* b_smem, size_t b_bytes,
                                            int tid, int nthreads) {
   using BT = typename std::conditional<kTf32, float, OT>::type;
+  if constexpr (!kTf32 && BS_B_NMAJOR) {
+    // 16-bit maps: B is an N-MAJOR operand (channels contiguous, as the features are stored) in the no-swizzle
+    // canonical layout ((8 ch, 1, n), (8 k, groups)) : 8 k-rows x 16 bytes per core matrix, channel chunks 128 B
+    // apart (SBO), k-groups c_tile*16 B apart (LBO).  Staging is a pure 16-byte copy, no conversion, no transposition:
+    // item q = (k-group, channel chunk, row) goes to byte 16*q; a warp reads 8 feature rows x 64 contiguous bytes.
+    static_assert(kTf32 || (sizeof(FT) == 2 && std::is_same<FT, OT>::value), "16-bit staging copies raw elements");
+    const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
+    const int cq8 = p.c_tile >> 3;
+    const int items = p.Kp * cq8;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 7) == 0;
+    uint4* dst = reinterpret_cast<uint4*>(b_smem);
+    constexpr int kBatch = 4;
+    for (int q0 = tid; q0 < items; q0 += kBatch * nthreads) {
+      uint4 v[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int q = q0 + b * nthreads;
+        const int g = q >> 3, kg = g / cq8;
+        const int k = kg * 8 + (q & 7) - kTcKOff, ch = c0 + (g - kg * cq8) * 8;      // operand row k' = k + kTcKOff
+        v[b] = make_uint4(0u, 0u, 0u, 0u);
+        if (q < items && k >= 0 && k < p.K && ch < p.C) {
+          const FT* src = f + (size_t)k * p.C + ch;
+          if (vec_ok) {
+            v[b] = __ldg(reinterpret_cast<const uint4*>(src));
+          } else {
+            FT e[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) e[cc] = ch + cc < p.C ? __ldg(src + cc) : Cvt<FT>::from(0.0f);
+            v[b] = *reinterpret_cast<const uint4*>(e);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b)
+        if (q0 + b * nthreads < items) dst[q0 + b * nthreads] = v[b];
+    }
+    return;
+  }
   // features [K, C] (c contiguous) -> K-major operand rows: item (kc, c) = the T k-values kc*T .. kc*T+T-1 of
   // channel c as one 16-byte chunk.  One thread moves a T x VC block: T 128-bit global loads (VC adjacent
   // channels of one feature row each, coalesced across the warp), transposed in registers into VC items.
@@ -672,7 +715,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // ========================================= MMA issue =========================================
       if (lane == 0) {
         const int buf = unit_it % nb, rnd = unit_it / nb;      // this unit's slot of the B ring
-        const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<OT, __half>::value ? 0u : 1u), (uint32_t)c_half);
+        const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<OT, __half>::value ? 0u : 1u), (uint32_t)c_half,
+                                          (!kTf32 && BS_B_NMAJOR) ? 1u : 0u);
         const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_stride);
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
         mbar_wait(&bars->b_full[buf], rnd & 1);
