@@ -57,6 +57,9 @@
 #ifndef BS_B_NMAJOR
 #define BS_B_NMAJOR 1         // 16-bit maps: N-major B operand (raw 16-byte copies) instead of K-major (transposed)
 #endif
+#ifndef BS_SCORE_LOADS
+#define BS_SCORE_LOADS 20
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
@@ -505,15 +508,18 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           const OT* sc = reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn + (size_t)(live ? pix : 0) * p.sp;
           const int k_split = kHalves == 2 ? (p.K >> 1) : 0;
           const int k_lo = half ? 0 : k_split, k_hi = half ? k_split : p.K;
-          int k = k_lo;
-          for (; k + 8 <= k_hi; k += 8) {
-            float v[8];
+          // up to kLd planes in flight per lane: the loads are the tile's latency chain (one round trip for the
+          // 16-17 planes a warp owns at K = 33, two at K = 65)
+          constexpr int kLd = BS_SCORE_LOADS;
+          for (int k = k_lo; k < k_hi; k += kLd) {
+            OT v[kLd];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)(k + j) * p.sk)) : 0.0f;
+            for (int j = 0; j < kLd; ++j)
+              v[j] = (live && k + j < k_hi) ? __ldg(sc + (size_t)(k + j) * p.sk) : Cvt<OT>::from(0.0f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) my[k + j] = v[j];
+            for (int j = 0; j < kLd; ++j)
+              if (k + j < k_hi) my[k + j] = (float)Cvt<OT>::to(v[j]);
           }
-          for (; k < k_hi; ++k) my[k] = live ? (float)Cvt<OT>::to(__ldg(sc + (size_t)k * p.sk)) : 0.0f;
         } else {
           float T = 1.0f;
           const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE;
