@@ -60,11 +60,21 @@
 #ifndef BS_SCORE_LOADS
 #define BS_SCORE_LOADS 20
 #endif
+#ifndef BS_TIMING
+#define BS_TIMING 0
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
 #ifndef BS_RNA_CUSTOM
 #define BS_RNA_CUSTOM 1
+#endif
+
+#if BS_TIMING
+__device__ unsigned long long g_tc_timing[16];   // clock64 stamps of CTA 0 (debug builds only)
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) ::g_tc_timing[i] = clock64(); } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
 #endif
 
 namespace blobsplat {
@@ -280,7 +290,7 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
     const int items = p.Kp * cq8;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 7) == 0;
     uint4* dst = reinterpret_cast<uint4*>(b_smem);
-    constexpr int kBatch = 4;
+    constexpr int kBatch = 8;     // 128 bytes in flight per thread: one round trip for a 30 KB operand on 256 threads
     for (int q0 = tid; q0 < items; q0 += kBatch * nthreads) {
       uint4 v[kBatch];
 #pragma unroll
@@ -365,6 +375,7 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
 template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores, bool kRing>
 __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32, 1) render_tc_kernel(const __grid_constant__ RenderTcLevels L) {
   const RenderTcParams& p0 = L.lv[0];     // Kp, c_tile and the dtypes are the same for every level
+  if (threadIdx.x == 0) TC_STAMP(0);
   constexpr int kTcComputeWarps = 4 * kHalves;
   constexpr int kTcComputeThreads = kTcComputeWarps * 32;
   constexpr int kTcMmaWarp = kTcComputeWarps + 4;
@@ -406,6 +417,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  if (threadIdx.x == 0) TC_STAMP(1);
   const uint32_t tmem_a = tmem + (uint32_t)p0.c_tile;             // A hi; A lo follows at + Kp/kACols columns
   const int a_cols = p0.Kp / kACols;
 
@@ -452,6 +464,19 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // instructions).  A warp still covers the same 32 consecutive pixels, so the composed-map stores stay coalesced.
       const int ppx = kTf32 ? q * 32 + ((lane & 15) << 1) + (lane >> 4) : px;
       asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
+      // stage 3 from score maps: the planes of this warp, and the first tile's loads issued BEFORE the operand staging
+      // so that the two global round trips of a unit's start overlap
+      constexpr int kLd = BS_SCORE_LOADS;
+      const int k_split = kHalves == 2 ? (p.K >> 1) : 0;
+      const int k_lo = half ? 0 : k_split, k_hi = half ? k_split : p.K;
+      OT pre[kFromScores ? kLd : 1];
+      if constexpr (kFromScores) {
+        const int pix0 = t_lo * kTcTileM + ppx;
+        const OT* sc0 = reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn + (size_t)(pix0 < P ? pix0 : 0) * p.sp;
+#pragma unroll
+        for (int j = 0; j < kLd; ++j)
+          pre[j] = (pix0 < P && k_lo + j < k_hi) ? __ldg(sc0 + (size_t)(k_lo + j) * p.sk) : Cvt<OT>::from(0.0f);
+      }
       uint32_t my_general = 0;
       if constexpr (!kFromScores)
       for (int i = ctid; i < p.M; i += kTcComputeThreads) {
@@ -471,6 +496,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
         mbar_arrive(&bars->b_full[0]);
       }
+      if (ctid == 0 && unit_it == 0) TC_STAMP(2);      // operands staged
       uint32_t any_general;   // barrier + OR-reduce: coef visible to all compute threads; does any blob need the slow form?
       asm volatile(
           "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
@@ -506,12 +532,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           // stand-alone stage 3: this pixel's K weights come from global memory (plane-contiguous, coalesced
           // across lanes for [N,K,H,W]); the two warps of a quarter split the planes
           const OT* sc = reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn + (size_t)(live ? pix : 0) * p.sp;
-          const int k_split = kHalves == 2 ? (p.K >> 1) : 0;
-          const int k_lo = half ? 0 : k_split, k_hi = half ? k_split : p.K;
           // up to kLd planes in flight per lane: the loads are the tile's latency chain (one round trip for the
           // 16-17 planes a warp owns at K = 33, two at K = 65)
-          constexpr int kLd = BS_SCORE_LOADS;
-          for (int k = k_lo; k < k_hi; k += kLd) {
+          if (t == 0) {
+#pragma unroll
+            for (int j = 0; j < kLd; ++j)
+              if (k_lo + j < k_hi) my[k_lo + j] = (float)Cvt<OT>::to(pre[j]);
+          }
+          for (int k = k_lo + (t == 0 ? kLd : 0); k < k_hi; k += kLd) {
             OT v[kLd];
 #pragma unroll
             for (int j = 0; j < kLd; ++j)
@@ -592,6 +620,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           }
         }
         if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
+        if (ctid == 0 && tile_it == 0) TC_STAMP(3);    // first tile's weights in the stash
 
         if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
         tc_fence_after();
@@ -637,6 +666,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->a_full);
+        if (ctid == 0 && tile_it == 0) TC_STAMP(4);    // first A in TMEM
         if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
       }
     } else if (warp < kTcComputeWarps + 4) {
@@ -650,6 +680,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&bars->d_full[h], tile_it & 1);
+          if (q == 0 && tile_it == 0) TC_STAMP(5 + h);   // first D half ready
           tc_fence_after();
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
           OT* const o = out + (size_t)(h * c_half) * P + pix;   // this pixel in the half's first channel plane
@@ -714,6 +745,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             }
           }
           tc_fence_before();
+          if (q == 0 && tile_it == 0) TC_STAMP(7 + h);   // first D half drained
           mbar_arrive(&bars->d_empty[h]);
         }
       }
@@ -774,6 +806,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(9);
   if (warp == kTcMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }

@@ -81,3 +81,9 @@ int feature_splat_levels_tc_dispatch(int n_levels, const void* const* scores, co
 }
 
 }  // namespace blobsplat
+
+#if BS_TIMING
+extern "C" __attribute__((visibility("default"))) int blobsplat_debug_timing(unsigned long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, ::g_tc_timing, sizeof(unsigned long long) * 16);
+}
+#endif
