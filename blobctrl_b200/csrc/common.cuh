@@ -144,12 +144,15 @@ constexpr float kLog2e = 1.4426950408889634f;
 
 // ---- per-blob coefficients, built once per (image, blob) in fp64 and staged in shared memory -------
 // Whitened form: q*log2(e) = u^2 + v^2, u = p*dx, v = r*dx + t*dy, dx/dy in pixels
-// relative to the centre, which is kept as a hi+lo float pair so (x - cx) carries no fp32
-// cancellation error.  Non-positive-definite covariances (never produced by the reference's
-// callers) take the general quadratic form qa*dx^2 + qb*dx*dy + qc*dy^2 instead.
+// relative to the centre.  The centre is a hi+lo float pair so (x - cx) carries no fp32 cancellation error; the
+// lo parts are folded into per-blob constants: with dxh = x - cx_hi, dyh = y - cy_hi (exact-ish differences)
+//   u = fma(p, dxh, u0),  v = fma(r, dxh, fma(t, dyh, v0)),  u0 = -p*cx_lo,  v0 = -(r*cx_lo + t*cy_lo)
+// — 2 FADD + 3 FFMA per pixel and blob.  Non-positive-definite covariances (never produced by the reference's
+// callers) take the general quadratic form qa*dx^2 + qb*dx*dy + qc*dy^2 instead, with (u0, v0) = (cx_lo, cy_lo).
 struct __align__(16) BlobCoef {
-  float cx_hi, cx_lo, cy_hi, cy_lo;
+  float cx_hi, cy_hi;
   float p, r, t;      // whitened (or qa, qb, qc when c0 == kC0General)
+  float u0, v0;       // folded centre residuals (or cx_lo, cy_lo when c0 == kC0General)
   float c0;           // exponent offset AND blob kind: see below
 };
 // c0 is the constant folded into the exponent, q' - 1 = u^2 + v^2 + c0, and doubles as the blob's kind:
@@ -167,8 +170,8 @@ __device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double 
   BlobCoef o;
   // centre in pixels: utils.py:138 (square) / :147 (tuple) — xs*W, ys*H
   const double cx = xs * (double)W, cy = ys * (double)H;
-  o.cx_hi = (float)cx; o.cx_lo = (float)(cx - (double)o.cx_hi);
-  o.cy_hi = (float)cy; o.cy_lo = (float)(cy - (double)o.cy_hi);
+  o.cx_hi = (float)cx; o.cy_hi = (float)cy;
+  const double cx_lo = cx - (double)o.cx_hi, cy_lo = cy - (double)o.cy_hi;
   // q = delta^T Sigma^-1 delta with delta = (dx/W, dy/H): only the symmetric part of Sigma^-1 matters.
   const double det = c00 * c11 - c01 * c10;
   const double l2e = 1.4426950408889634;
@@ -177,12 +180,14 @@ __device__ __forceinline__ BlobCoef make_blob_coef(double xs, double ys, double 
   const double C = l2e * (c00 / det) / ((double)H * (double)H);
   const double schur = A - (B * B) / C;
   if (size < 0.5f) {
-    o.p = o.r = o.t = 0.0f; o.c0 = kC0Gated;
+    o.p = o.r = o.t = o.u0 = o.v0 = 0.0f; o.c0 = kC0Gated;
   } else if (C > 0.0 && schur > 0.0) {
     const double t = sqrt(C);
     o.t = (float)t; o.r = (float)(B / t); o.p = (float)sqrt(schur); o.c0 = kC0Normal;
+    o.u0 = (float)(-(double)o.p * cx_lo); o.v0 = (float)(-((double)o.r * cx_lo + (double)o.t * cy_lo));
   } else {
     o.p = (float)A; o.r = (float)(2.0 * B); o.t = (float)C; o.c0 = kC0General;
+    o.u0 = (float)cx_lo; o.v0 = (float)cy_lo;
   }
   return o;
 }
@@ -197,8 +202,8 @@ __device__ __forceinline__ BlobCoef make_blob_coef_ellipse(double xc, double yc,
                                                            float size, double img_w, double img_h, int H, int W) {
   BlobCoef o;
   const double cx = xc / img_w * (double)W, cy = yc / img_h * (double)H;
-  o.cx_hi = (float)cx; o.cx_lo = (float)(cx - (double)o.cx_hi);
-  o.cy_hi = (float)cy; o.cy_lo = (float)(cy - (double)o.cy_hi);
+  o.cx_hi = (float)cx; o.cy_hi = (float)cy;
+  const double cx_lo = cx - (double)o.cx_hi, cy_lo = cy - (double)o.cy_hi;
   double a1 = 180.0 - angle_deg; a1 -= 180.0 * floor(a1 / 180.0);            // python's % 180
   double a2 = a1 + 90.0; a2 -= 180.0 * floor(a2 / 180.0);
   const double th = a2 * 0.017453292519943295;
@@ -210,7 +215,8 @@ __device__ __forceinline__ BlobCoef make_blob_coef_ellipse(double xc, double yc,
   const double Bq = m00 * m01 + m10 * m11, Cq = m01 * m01 + m11 * m11;
   const double t = sqrt(Cq);
   o.t = (float)t; o.r = (float)(Bq / t); o.p = (float)(fabs(m00 * m11 - m01 * m10) / t); o.c0 = kC0Normal;
-  if (size < 0.5f) { o.p = o.r = o.t = 0.0f; o.c0 = kC0Gated; }
+  o.u0 = (float)(-(double)o.p * cx_lo); o.v0 = (float)(-((double)o.r * cx_lo + (double)o.t * cy_lo));
+  if (size < 0.5f) { o.p = o.r = o.t = o.u0 = o.v0 = 0.0f; o.c0 = kC0Gated; }
   return o;
 }
 
@@ -232,23 +238,22 @@ __device__ __forceinline__ float opacity_from_q2m1(float q2m1) {
 
 // branch-free form for positive-definite blobs (the only kind the reference's callers produce)
 __device__ __forceinline__ float blob_opacity_pd(const BlobCoef& c, float xf, float yf) {
-  const float dy = (yf - c.cy_hi) - c.cy_lo;
-  const float dx = (xf - c.cx_hi) - c.cx_lo;
-  const float u = c.p * dx;
-  const float v = fmaf(c.r, dx, c.t * dy);
+  const float dyh = yf - c.cy_hi, dxh = xf - c.cx_hi;
+  const float u = fmaf(c.p, dxh, c.u0);
+  const float v = fmaf(c.r, dxh, fmaf(c.t, dyh, c.v0));
   return opacity_from_q2m1(fmaf(u, u, fmaf(v, v, c.c0)));   // gated blobs: u = v = 0, c0 = log2(1e6 - 0.5)
 }
 
 // raw opacity of one blob at one pixel (stage 1 + gate)
 __device__ __forceinline__ float blob_opacity(const BlobCoef& c, float xf, float yf) {
   if (coef_gated(c)) return 1e-6f;
-  const float dy = (yf - c.cy_hi) - c.cy_lo;
-  const float dx = (xf - c.cx_hi) - c.cx_lo;
+  const float dyh = yf - c.cy_hi, dxh = xf - c.cx_hi;
   if (!coef_general(c)) {
-    const float u = c.p * dx;
-    const float v = fmaf(c.r, dx, c.t * dy);
+    const float u = fmaf(c.p, dxh, c.u0);
+    const float v = fmaf(c.r, dxh, fmaf(c.t, dyh, c.v0));
     return opacity_from_q2(fmaf(u, u, v * v));
   }
+  const float dx = dxh - c.u0, dy = dyh - c.v0;          // general form: (u0, v0) = (cx_lo, cy_lo)
   return opacity_from_q2(fmaf(dx, fmaf(c.p, dx, c.r * dy), c.t * dy * dy));
 }
 

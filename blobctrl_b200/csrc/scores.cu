@@ -77,11 +77,10 @@ scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys
 #pragma unroll
         for (int j = 0; j < V; ++j) s[j] = 1e-6f;
       } else {
-        const float dy = (yf - c.cy_hi) - c.cy_lo;
-        const float dx0 = (xf - c.cx_hi) - c.cx_lo;
+        const float dyh = yf - c.cy_hi, dxh = xf - c.cx_hi;
         if (!coef_general(c)) {
-          const float u0 = c.p * dx0;
-          const float v0 = fmaf(c.r, dx0, c.t * dy);
+          const float u0 = fmaf(c.p, dxh, c.u0);
+          const float v0 = fmaf(c.r, dxh, fmaf(c.t, dyh, c.v0));
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const float u = fmaf((float)j, c.p, u0);
@@ -89,6 +88,7 @@ scores_lane_pixel_f32(const float* __restrict__ xs, const float* __restrict__ ys
             s[j] = opacity_from_q2m1(fmaf(u, u, fmaf(v, v, -1.0f)));
           }
         } else {
+          const float dx0 = dxh - c.u0, dy = dyh - c.v0;     // general form: (u0, v0) = (cx_lo, cy_lo)
 #pragma unroll
           for (int j = 0; j < V; ++j) {
             const float dx = dx0 + (float)j;
