@@ -63,6 +63,12 @@
 #ifndef BS_TIMING
 #define BS_TIMING 0
 #endif
+#ifndef BS_SPLIT_NUM
+#define BS_SPLIT_NUM 7          // back range's share of the blobs, in 16ths (it also carries the rescale pass)
+#endif
+#ifndef BS_SPLIT_ALIGN
+#define BS_SPLIT_ALIGN 8        // both blob ranges are whole groups of this many blobs when M allows
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
@@ -80,7 +86,7 @@ __device__ unsigned long long g_tc_timing[16];   // clock64 stamps of CTA 0 (deb
 namespace blobsplat {
 
 // kHalves = 1: 4 compute warps (one per TMEM lane quarter); kHalves = 2: 8 compute warps, two per quarter, each
-// compositing one of two blob ranges.  Threads = (4*kHalves compute + 4 epilogue + 1 MMA) warps = 288 / 416.
+// compositing one of two blob ranges.  Threads = (4*kHalves compute + 4 epilogue + 1 MMA) warps = 288 / 416 (+ 3 staging warps = 512 in the kRing instantiations).
 constexpr int kTcTileM = 128;
 constexpr int kTcMaxCTile = 320;
 // Plane k (0 = background, m+1 = blob m) lives at operand row / TMEM column / stash column k + kTcKOff: with the
@@ -120,18 +126,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
-#ifdef BS_PREV_WAIT
-  (void)spins;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-#else
   while (!mbar_try_wait(bar, parity)) {
     if (BS_SPIN_SLEEP_NS > 0) __nanosleep(BS_SPIN_SLEEP_NS);
     if (((++spins) & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
   }
-#endif
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -506,12 +504,6 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // Two-level multiplicative suffix scan across blobs: each range is composited with a local
       // transmittance; the back range is then scaled by the front range's total transmittance.
       // The back range carries the extra rescale pass, so it gets the smaller share (7/16) of the blobs.
-#ifndef BS_SPLIT_NUM
-#define BS_SPLIT_NUM 7
-#endif
-#ifndef BS_SPLIT_ALIGN
-#define BS_SPLIT_ALIGN 8
-#endif
       // front range = M - m_split blobs: both ranges are whole groups of 8 whenever M is (no serial tail blobs; the
       // serial tail costs ~2.3x per blob), and the back range stays the smaller one because it also rescales
       int m_split = 0;
