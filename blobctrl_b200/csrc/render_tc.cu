@@ -1,6 +1,6 @@
 // Fused render (stages 1+2+3) — instantiations of render_tc.cuh with the A operand rendered from blob
 // parameters.  Kernel, pipeline and layout notes: render_tc.cuh.
-#include "render_tc.cuh"
+#include "render_tc2.cuh"
 
 namespace blobsplat {
 
@@ -24,6 +24,10 @@ int render_tc_dispatch(const float* xs, const float* ys, const float* covs, cons
   if (!pl.ok) BS_UNSUPPORTED("fused render: %s", pl.why);
   RenderTcParams p{};
   p.xs = xs; p.ys = ys; p.covs = covs; p.sizes = sizes; p.feats = features; p.composed = composed; p.grid = grid;
+  if (render_tc2_usable(out_dtype, H, W, composed, grid, nullptr, 0, 0, 1)) {   // 16-bit maps: two pixels per lane
+    const Tc2Plan pl2 = plan_tc2(M + 1, C);
+    if (pl2.ok) return run_tc2<false>(p, pl2, N, M + 1, H, W, C, out_dtype, st);
+  }
   if (int rc = fill_tc_units(p, pl, N, M + 1, H, W, C)) return rc;
   return launch_tc_dtype<false>(p, pl.smem, out_dtype, st);
 }

@@ -245,6 +245,7 @@ struct RenderTcParams {
   int K, Kp;              // K = M + 1; Kp = K rounded up to the MMA k-step (8 tf32 / 16 f16)
   int c_tile, c_chunks;   // channels per work unit (multiple of 32, <= 320); ceil(C / c_tile)
   int tiles_per_image;    // 128-pixel tiles per image
+  int cw;                 // render_tc2 only: channels per drain sub-step
   int nb;                 // B operand buffers in shared memory (ring); > 1: the staging warps run ahead of the units
   int smem_bytes;         // dynamic shared memory of the launch (fixed part + nb B slots)
   int whole_runs;         // schedule: whole (image, chunk) runs round-robin vs contiguous equal tile ranges
@@ -837,11 +838,11 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
 }
 
 // Fill the shape / work-unit fields shared by both A sources.
-static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int H, int W, int C) {
+static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int H, int W, int C, int tile_px = kTcTileM) {
   p.N = N; p.M = K - 1; p.H = H; p.W = W; p.C = C; p.K = K; p.Kp = pl.Kp;
   p.c_tile = pl.c_tile; p.c_chunks = (C + pl.c_tile - 1) / pl.c_tile;
   const int P = H * W;
-  p.tiles_per_image = (P + kTcTileM - 1) / kTcTileM;
+  p.tiles_per_image = (P + tile_px - 1) / tile_px;
   const long long total = (long long)N * p.c_chunks * p.tiles_per_image;
   if (total > 0x7fffffffll) BS_UNSUPPORTED("too many tiles for one launch");
   p.total_tiles = (int)total;
@@ -849,6 +850,7 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ctas = std::min(sms, p.total_tiles);
+  const int tw = tile_px / kTcTileM;                           // cost of a tile in 128-pixel tiles
   long long ranges = 0;                                        // worst CTA under equal tile ranges
   int range_units = 0;
   for (int i = 0; i < ctas; ++i) {
@@ -856,11 +858,11 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
     if (hi <= lo) continue;
     const int units = (hi - 1) / p.tiles_per_image - lo / p.tiles_per_image + 1;
     range_units = std::max(range_units, units);
-    ranges = std::max<long long>(ranges, (hi - lo) + 2ll * BS_STAGE_COST * units);   // staggered stagings queue behind other CTAs' stores: twice the cost
+    ranges = std::max<long long>(ranges, (long long)(hi - lo) * tw + 2ll * BS_STAGE_COST * units);   // staggered stagings queue behind other CTAs' stores: twice the cost
   }
   const long long runs = total / p.tiles_per_image;
   const long long whole_units = ctas > 0 ? (runs + ctas - 1) / ctas : 0;
-  const long long whole = whole_units * (p.tiles_per_image + BS_STAGE_COST);
+  const long long whole = whole_units * ((long long)p.tiles_per_image * tw + BS_STAGE_COST);
   p.whole_runs = whole <= ranges ? 1 : 0;
   // B ring + staging warps only where a CTA has enough units for staging to run ahead of; with one or two units per
   // CTA the 256 compute threads stage faster than the 96 staging threads and there is nothing to overlap with

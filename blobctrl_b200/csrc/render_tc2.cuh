@@ -1,0 +1,469 @@
+// Fused render for 16-bit maps, two pixels per lane — same pipeline as render_tc.cuh (read that first), different
+// tile geometry.  Why: with one pixel per TMEM lane a warp owns 32 pixels = 64 bytes of a bf16/f16 plane, so every
+// store of the drain and of the composed maps is a half line and each value costs a convert + an extract + a store.
+// Here a tile is 256 consecutive pixels and lane r holds the ADJACENT pixels 2r and 2r+1:
+//
+//   * two A operands in tensor memory (even pixels / odd pixels), two MMAs per k-step that share B:
+//       D_even[lane, c] = sum_k A_even[lane, k] B[k, c]      D_odd likewise, in the next cw columns
+//   * the drain packs (D_even, D_odd) of a channel into one 32-bit word: one convert + one store per TWO values, and a
+//     warp writes 64 pixels = one whole 128-byte line;
+//   * the composed maps leave stages 1+2 the same way (one packed 32-bit store per plane and lane);
+//   * stages 1+2 share the row terms between the two pixels: per blob 2 FADD + 3 FFMA for the first pixel and
+//     2 FADD for the second (u + p, v + r) instead of 2 x (2 FADD + 3 FFMA);
+//   * the channel tile is drained in nsub sub-steps of cw channels (2*cw accumulator columns, two slots) so that the MMAs
+//     of sub-step j+1 overlap the drain of sub-step j:  TMEM = 4*cw (D) + Kp (A even + odd) <= 512 columns.
+//
+// Preconditions (checked on the host, render_tc2_usable): 16-bit maps, W even (the two pixels of a lane share a row),
+// output bases 4-byte aligned, score maps pixel-contiguous with even strides.  Everything else stays on render_tc.cuh.
+#pragma once
+#include "render_tc.cuh"
+
+#ifndef BS_PX2
+#define BS_PX2 1               // 16-bit maps: use the two-pixels-per-lane kernel where its preconditions hold
+#endif
+
+namespace blobsplat {
+
+constexpr int kTc2TilePx = 2 * kTcTileM;   // 256 pixels per tile
+
+// both pixels of a lane (x, x+1 on one row) against one positive-definite blob
+__device__ __forceinline__ void blob_opacity_pd2(const BlobCoef& c, float xf, float yf, float& sa, float& sb) {
+  const float dyh = yf - c.cy_hi, dxh = xf - c.cx_hi;
+  const float tv = fmaf(c.t, dyh, c.v0);
+  const float ua = fmaf(c.p, dxh, c.u0), va = fmaf(c.r, dxh, tv);
+  const float ub = ua + c.p, vb = va + c.r;
+  sa = opacity_from_q2m1(fmaf(ua, ua, fmaf(va, va, c.c0)));
+  sb = opacity_from_q2m1(fmaf(ub, ub, fmaf(vb, vb, c.c0)));
+}
+
+template <typename OT>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {   // low half = a (even pixel)
+  if constexpr (std::is_same<OT, __nv_bfloat16>::value) {
+    const __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
+  } else {
+    const __half2 t = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&t);
+  }
+}
+template <typename OT>
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+  if constexpr (std::is_same<OT, __nv_bfloat16>::value) {
+    const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w);
+    a = __low2float(t); b = __high2float(t);
+  } else {
+    const __half2 t = *reinterpret_cast<const __half2*>(&w);
+    a = __low2float(t); b = __high2float(t);
+  }
+}
+// two adjacent pixels of one plane
+template <typename OT>
+__device__ __forceinline__ void store_px2(OT* p, float a, float b, bool pred) {
+  const uint32_t w = pack2<OT>(a, b);
+  if (pred) __stcs(reinterpret_cast<unsigned int*>(p), w);
+}
+
+// 16 channel planes of this lane's two pixels: e[i] / o[i] = fp32 accumulators of the even / odd pixel
+template <typename OT>
+__device__ __forceinline__ void drain16(OT* oc, size_t P, const uint32_t* e, const uint32_t* o, bool live, int left) {
+  if (left >= 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) store_px2<OT>(oc + (size_t)i * P, __uint_as_float(e[i]), __uint_as_float(o[i]), live);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) store_px2<OT>(oc + (size_t)i * P, __uint_as_float(e[i]), __uint_as_float(o[i]), live && i < left);
+  }
+}
+
+template <typename OT, int kP, bool kFromScores, bool kRing>
+__global__ void __launch_bounds__((13 + (kRing ? kTcStageWarps : 0)) * 32, 1)
+render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
+  const RenderTcParams& p = L.lv[0];
+  constexpr int kComputeWarps = 8, kComputeThreads = 256, kMmaWarp = 12;
+  extern __shared__ __align__(1024) unsigned char smem[];
+
+  const int P = kP > 0 ? kP : p.H * p.W;
+  const int cw = p.cw, nsub = p.c_tile / cw;                              // drain sub-steps of cw channels
+  const size_t b_bytes = (size_t)(p.Kp / 8) * p.c_tile * 16;             // one B buffer (N-major, see tc_stage_b)
+  const int nb = kRing ? p.nb : 1;
+  unsigned char* b_smem = smem;
+  const int srow = p.Kp + 4;
+  float* stash = reinterpret_cast<float*>(smem + (size_t)nb * b_bytes);  // [2 parities][128 lanes][Kp + 4]
+  float* carry = stash + (size_t)2 * kTcTileM * srow;                    // [2][128] front-range transmittances
+  BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + 2 * kTcTileM);
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      mbar_init(&bars->a_full, kComputeThreads); mbar_init(&bars->a_free, 1);
+      for (int i = 0; i < kTcMaxB; ++i) {
+        mbar_init(&bars->b_full[i], kRing ? kTcStageWarps * 32 : kComputeThreads); mbar_init(&bars->b_free[i], 1);
+      }
+      mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
+      mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  const uint32_t tmem_a = tmem + (uint32_t)(4 * cw);     // A even; A odd follows at + a_cols
+  const int a_cols = p.Kp / 2;                           // two k per 32-bit column
+
+  int unit_it = 0, tile_it = 0;
+  int sub_it = 0;                                        // drain sub-steps so far (slot = sub_it & 1)
+
+  const bool whole_runs = p.whole_runs;
+  const int g_end = whole_runs ? p.total_tiles : tc_range_begin(p.total_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
+  for (int gs = whole_runs ? (int)blockIdx.x * p.tiles_per_image : tc_range_begin(p.total_tiles, (int)blockIdx.x, (int)gridDim.x);
+       gs < g_end; ++unit_it) {
+    const int img_chunk = gs / p.tiles_per_image;
+    const int n = img_chunk / p.c_chunks;
+    const int chunk = img_chunk - n * p.c_chunks;
+    const int c0 = chunk * p.c_tile;
+    const int t_lo = gs - img_chunk * p.tiles_per_image;
+    const int ntiles = min(p.tiles_per_image - t_lo, g_end - gs);
+    gs += ntiles;
+    if (whole_runs) gs += ((int)gridDim.x - 1) * p.tiles_per_image;
+
+    if (warp < kComputeWarps) {
+      // =============================== stages 1+2 (two pixels per lane) ===============================
+      const int ctid = warp * 32 + lane;
+      const int half = warp >> 2, q = warp & 3;
+      const int row = q * 32 + lane;                       // TMEM lane / stash row; pixels 2*row, 2*row + 1 of the tile
+      asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
+      constexpr int kLd = BS_SCORE_LOADS;
+      const int k_split = p.K >> 1;
+      const int k_lo = half ? 0 : k_split, k_hi = half ? k_split : p.K;
+      const long long sk2 = p.sk >> 1;                     // plane stride in 32-bit words (pixel pairs)
+      uint32_t pre[kFromScores ? kLd : 1];
+      if constexpr (kFromScores) {
+        const int pix0 = t_lo * kTc2TilePx + 2 * row;
+        const uint32_t* sc0 = reinterpret_cast<const uint32_t*>(reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn +
+                                                                (pix0 < P ? pix0 : 0));
+#pragma unroll
+        for (int j = 0; j < kLd; ++j) pre[j] = (pix0 < P && k_lo + j < k_hi) ? __ldg(sc0 + (size_t)(k_lo + j) * sk2) : 0u;
+      }
+      uint32_t my_general = 0;
+      if constexpr (!kFromScores)
+        for (int i = ctid; i < p.M; i += kComputeThreads) {
+          const size_t b = (size_t)n * p.M + i;
+          const float* c = p.covs + 4 * b;
+          const BlobCoef bc = make_blob_coef((double)p.xs[b], (double)p.ys[b], (double)c[0], (double)c[1], (double)c[2],
+                                             (double)c[3], p.sizes[b], p.H, p.W);
+          my_general |= coef_general(bc) ? 1u : 0u;
+          coef[i] = bc;
+        }
+      if (unit_it == 0)      // stash columns that are never written stay zero for the whole kernel
+        for (int i = ctid; i < 2 * kTcTileM * srow; i += kComputeThreads) stash[i] = 0.0f;
+      if constexpr (!kRing) {
+        if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
+        tc_stage_b<OT, OT, false>(p, n, c0, b_smem, b_bytes, ctid, kComputeThreads);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(&bars->b_full[0]);
+      }
+      uint32_t any_general;
+      asm volatile(
+          "{\n\t.reg .pred q, r;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+          "barrier.cta.red.or.pred r, 1, %2, q;\n\tselp.u32 %0, 1, 0, r;\n\t}"
+          : "=r"(any_general) : "r"(my_general), "n"(kComputeThreads) : "memory");
+
+      const int m_split = ((p.M * BS_SPLIT_NUM) >> 4) & ~7;       // back range (it also rescales): the smaller share
+      const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
+      const int pair_bar = 2 + q;
+      OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
+      float* const my_e = stash + (size_t)row * srow + kTcKOff;   // my_e[k] = plane k of the even pixel
+      float* const my_o = my_e + (size_t)kTcTileM * srow;
+      for (int t = 0; t < ntiles; ++t, ++tile_it) {
+        const int pix0 = (t_lo + t) * kTc2TilePx + 2 * row;
+        const bool live = pix0 < P;                           // P even: both pixels or none
+        const int y = live ? pix0 / p.W : 0;
+        const float xf = (float)(live ? pix0 - y * p.W : 0), yf = (float)y;
+        if constexpr (kFromScores) {
+          const uint32_t* sc = reinterpret_cast<const uint32_t*>(reinterpret_cast<const OT*>(p.scores) + (size_t)n * p.sn +
+                                                                 (live ? pix0 : 0));
+          if (t == 0) {
+#pragma unroll
+            for (int j = 0; j < kLd; ++j)
+              if (k_lo + j < k_hi) unpack2<OT>(pre[j], my_e[k_lo + j], my_o[k_lo + j]);
+          }
+          for (int k = k_lo + (t == 0 ? kLd : 0); k < k_hi; k += kLd) {
+            uint32_t v[kLd];
+#pragma unroll
+            for (int j = 0; j < kLd; ++j) v[j] = (live && k + j < k_hi) ? __ldg(sc + (size_t)(k + j) * sk2) : 0u;
+#pragma unroll
+            for (int j = 0; j < kLd; ++j)
+              if (k + j < k_hi) unpack2<OT>(v[j], my_e[k + j], my_o[k + j]);
+          }
+        } else {
+          float Ta = 1.0f, Tb = 1.0f;
+          const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE;
+          const bool wr_now = wr && half == 0;
+          OT* const comp_px = comp + pix0;
+          int m = m_hi;
+          // serial head until the remaining blobs of the range are whole, float4-aligned groups of 4
+          for (; m >= m_lo + 1 && (any_general || (m & 3) != 0 || m < m_lo + 4); --m) {
+            float sa, sb;
+            if (any_general) { sa = blob_opacity(coef[m - 1], xf, yf); sb = blob_opacity(coef[m - 1], xf + 1.0f, yf); }
+            else blob_opacity_pd2(coef[m - 1], xf, yf, sa, sb);
+            const float da = sa * Ta, db = sb * Tb;
+            Ta = fmaf(-sa, Ta, Ta); Tb = fmaf(-sb, Tb, Tb);
+            my_e[m] = da; my_o[m] = db;
+            store_px2<OT>(comp_px + (size_t)m * P, da, db, wr_now);
+          }
+          // branch-free: 4 blobs x 2 pixels in flight
+          for (; m >= m_lo + 4; m -= 4) {
+            float sa[4], sb[4], da[4], db[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) blob_opacity_pd2(coef[m - 1 - j], xf, yf, sa[j], sb[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              da[j] = sa[j] * Ta; Ta = fmaf(-sa[j], Ta, Ta);
+              db[j] = sb[j] * Tb; Tb = fmaf(-sb[j], Tb, Tb);
+            }
+            OT* const cp = comp_px + (size_t)m * P;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) store_px2<OT>(cp - (ptrdiff_t)j * P, da[j], db[j], wr_now);
+            *reinterpret_cast<float4*>(my_e + m - 3) = make_float4(da[3], da[2], da[1], da[0]);
+            *reinterpret_cast<float4*>(my_o + m - 3) = make_float4(db[3], db[2], db[1], db[0]);
+          }
+          for (; m >= m_lo + 1; --m) {
+            float sa, sb;
+            if (any_general) { sa = blob_opacity(coef[m - 1], xf, yf); sb = blob_opacity(coef[m - 1], xf + 1.0f, yf); }
+            else blob_opacity_pd2(coef[m - 1], xf, yf, sa, sb);
+            const float da = sa * Ta, db = sb * Tb;
+            Ta = fmaf(-sa, Ta, Ta); Tb = fmaf(-sb, Tb, Tb);
+            my_e[m] = da; my_o[m] = db;
+            store_px2<OT>(comp_px + (size_t)m * P, da, db, wr_now);
+          }
+          if (half == 0) { carry[row] = Ta; carry[kTcTileM + row] = Tb; }
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (half == 1) {
+            const float ca = carry[row], cb = carry[kTcTileM + row];
+            int k = m_hi;
+            for (; k >= 1 && ((k & 3) != 0 || k < 4); --k) {
+              const float va = my_e[k] * ca, vb = my_o[k] * cb;
+              my_e[k] = va; my_o[k] = vb;
+              store_px2<OT>(comp_px + (size_t)k * P, va, vb, wr);
+            }
+            for (; k >= 4; k -= 4) {
+              float4 a4 = *reinterpret_cast<const float4*>(my_e + k - 3), b4 = *reinterpret_cast<const float4*>(my_o + k - 3);
+              a4.x *= ca; a4.y *= ca; a4.z *= ca; a4.w *= ca;
+              b4.x *= cb; b4.y *= cb; b4.z *= cb; b4.w *= cb;
+              *reinterpret_cast<float4*>(my_e + k - 3) = a4;
+              *reinterpret_cast<float4*>(my_o + k - 3) = b4;
+              OT* const cp = comp_px + (size_t)k * P;
+              store_px2<OT>(cp, a4.w, b4.w, wr);
+              store_px2<OT>(cp - (ptrdiff_t)P, a4.z, b4.z, wr);
+              store_px2<OT>(cp - (ptrdiff_t)2 * P, a4.y, b4.y, wr);
+              store_px2<OT>(cp - (ptrdiff_t)3 * P, a4.x, b4.x, wr);
+            }
+            for (; k >= 1; --k) {
+              const float va = my_e[k] * ca, vb = my_o[k] * cb;
+              my_e[k] = va; my_o[k] = vb;
+              store_px2<OT>(comp_px + (size_t)k * P, va, vb, wr);
+            }
+            const float bga = Ta * ca, bgb = Tb * cb;          // background: alpha 1 * total transmittance
+            my_e[0] = bga; my_o[0] = bgb;
+            store_px2<OT>(comp_px, bga, bgb, wr);
+          }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash rows complete
+
+        if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
+        tc_fence_after();
+        const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+        for (int g = half; g < p.Kp / 16; g += 2) {          // the two warps of a quarter interleave the k-groups
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {
+            const float* src = (par ? my_o : my_e) - kTcKOff + g * 16;     // operand rows 16g .. 16g+15
+            const float4 q0 = *reinterpret_cast<const float4*>(src), q1 = *reinterpret_cast<const float4*>(src + 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(src + 8), q3 = *reinterpret_cast<const float4*>(src + 12);
+            const float wv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pk[j] = pack2<OT>(wv[2 * j], wv[2 * j + 1]);   // low half = even k
+            tmem_st8(tmem_a + lane_addr + (uint32_t)(par * a_cols + g * 8), pk);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->a_full);
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+      }
+    } else if (warp < kComputeWarps + 4) {
+      // ============================ drain: (even, odd) pixel pairs, 32-bit stores ============================
+      const int q = warp - kComputeWarps;
+      OT* const out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
+      const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
+      for (int t = 0; t < ntiles; ++t, ++tile_it) {
+        const int pix0 = (t_lo + t) * kTc2TilePx + 2 * (q * 32 + lane);
+        const bool live = pix0 < P && !BS_ABL_NO_EPI_STORE;
+#pragma unroll 1
+        for (int j = 0; j < nsub; ++j, ++sub_it) {
+          const int slot = sub_it & 1;
+          mbar_wait(&bars->d_full[slot], (sub_it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t te = tmem + lane_addr + (uint32_t)(slot * 2 * cw), to = te + (uint32_t)cw;
+          OT* const o = out + (size_t)(j * cw) * P + pix0;
+          const int chs = p.C - (c0 + j * cw);                 // valid channels from this sub-step on
+          uint32_t ea[16], oa[16], eb[16], ob[16];
+          tmem_ld16(te, ea); tmem_ld16(to, oa);
+          tmem_wait_ld();
+          for (int cc = 0; cc < cw; cc += 32) {
+            const bool more = cc + 16 < cw;
+            if (more) { tmem_ld16(te + cc + 16, eb); tmem_ld16(to + cc + 16, ob); }
+            drain16<OT>(o + (size_t)cc * P, (size_t)P, ea, oa, live, chs - cc);
+            tmem_wait_ld();
+            if (more) {
+              if (cc + 32 < cw) { tmem_ld16(te + cc + 32, ea); tmem_ld16(to + cc + 32, oa); }
+              drain16<OT>(o + (size_t)(cc + 16) * P, (size_t)P, eb, ob, live, chs - cc - 16);
+              tmem_wait_ld();
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bars->d_empty[slot]);
+        }
+      }
+    } else if (warp == kMmaWarp) {
+      // ========================================= MMA issue =========================================
+      if (lane == 0) {
+        const int buf = unit_it % nb, rnd = unit_it / nb;
+        const uint32_t idesc = make_idesc(std::is_same<OT, __half>::value ? 0u : 1u, (uint32_t)cw, 1u);
+        const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_bytes);
+        const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
+        mbar_wait(&bars->b_full[buf], rnd & 1);
+        for (int t = 0; t < ntiles; ++t, ++tile_it) {
+          mbar_wait(&bars->a_full, tile_it & 1);
+          tc_fence_after();
+          for (int j = 0; j < nsub; ++j, ++sub_it) {
+            const int slot = sub_it & 1;
+            if (sub_it >= 2) mbar_wait(&bars->d_empty[slot], ((sub_it >> 1) - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
+              const uint32_t d_addr = tmem + (uint32_t)(slot * 2 * cw + par * cw);
+              uint32_t acc = 0;
+              for (int ks = 0; ks < p.Kp / 16; ++ks) {
+                const uint32_t b_addr = b_base + (uint32_t)(2 * ks) * lbo + (uint32_t)(j * cw) * 16u;
+                if (!BS_ABL_NO_MMA)
+                  umma_ts<false>(d_addr, tmem_a + (uint32_t)(par * a_cols + ks * 8), make_b_desc(b_addr, lbo, sbo), idesc, acc);
+                acc = 1;
+              }
+            }
+            tc_commit(&bars->d_full[slot]);
+          }
+          tc_commit(&bars->a_free);
+        }
+        tc_commit(&bars->b_free[buf]);
+      }
+      __syncwarp();
+    } else if constexpr (kRing) {
+      const int buf = unit_it % nb, rnd = unit_it / nb;
+      if (rnd > 0) mbar_wait(&bars->b_free[buf], (rnd - 1) & 1);
+      tc_stage_b<OT, OT, false>(p, n, c0, b_smem + (size_t)buf * b_bytes, b_bytes, (int)threadIdx.x - (kMmaWarp + 1) * 32,
+                                kTcStageWarps * 32);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&bars->b_full[buf]);
+    }
+  }
+
+  if (warp == kMmaWarp && lane == 0 && tile_it > 0) {
+    mbar_wait(&bars->a_free, (tile_it - 1) & 1);
+    mbar_wait(&bars->b_free[(unit_it - 1) % nb], ((unit_it - 1) / nb) & 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct Tc2Plan { int Kp, c_tile, cw, nb; size_t smem, b_slot; bool ok; };
+
+static inline Tc2Plan plan_tc2(int K, int C) {
+  Tc2Plan pl{};
+  pl.ok = false;
+  if (K - 1 > kTcMaxBlobs || C % 32 != 0) return pl;
+  pl.Kp = round_up(K + kTcKOff, 16);
+  const size_t fixed = (size_t)2 * (pl.Kp + 4) * kTcTileM * 4 + 2 * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) +
+                       sizeof(TcBarriers) + 512;
+  const size_t per_c = (size_t)pl.Kp * 2;
+  if (fixed + per_c * 32 > kTcSmemBudget) return pl;
+  int c_tile = std::min(kTcMaxCTile, C);
+  c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
+  for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
+    if (C % c == 0) { c_tile = c; break; }
+  // drain sub-step: the widest multiple of 16 channels that divides the tile and leaves room for two 2*cw-column
+  // slots next to the two A operands
+  int cw = 0;
+  for (int w = 128; w >= 16; w -= 16)
+    if (c_tile % w == 0 && 4 * w + pl.Kp <= 512) { cw = w; break; }
+  if (cw == 0) return pl;
+  pl.c_tile = c_tile; pl.cw = cw;
+  pl.b_slot = per_c * c_tile;
+  pl.nb = (int)std::min<size_t>(BS_MAX_B, (kTcSmemBudget - fixed) / pl.b_slot);
+  pl.smem = fixed + (size_t)pl.nb * pl.b_slot;
+  pl.ok = pl.nb >= 1;
+  return pl;
+}
+
+// Can this 16-bit problem run on the two-pixels-per-lane kernel?
+static inline bool render_tc2_usable(int dtype, int H, int W, const void* composed, const void* grid, const void* scores,
+                                     long long sn, long long sk, long long sp) {
+  if (!BS_PX2 || !BS_B_NMAJOR || (dtype != BLOBSPLAT_BF16 && dtype != BLOBSPLAT_F16)) return false;
+  if ((W & 1) != 0 || (long long)H * W < kTc2TilePx) return false;      // small images: the 128-pixel tile wastes less
+  if (((reinterpret_cast<uintptr_t>(composed) | reinterpret_cast<uintptr_t>(grid)) & 3) != 0) return false;
+  if (scores && (sp != 1 || (sk & 1) != 0 || (sn & 1) != 0 || (reinterpret_cast<uintptr_t>(scores) & 3) != 0)) return false;
+  return true;
+}
+
+template <typename OT, int kP, bool kFromScores, bool kRing>
+static int launch_tc2_pr(const RenderTcParams& p, cudaStream_t st) {
+  static thread_local int configured_dev = -1, sm_count = 0;
+  int dev = 0;
+  BS_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    BS_CUDA(cudaFuncSetAttribute(render_tc2_kernel<OT, kP, kFromScores, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    configured_dev = dev;
+  }
+  const int grid = std::min(sm_count, p.total_tiles);
+  RenderTcLevels L{};
+  L.lv[0] = p;
+  L.n_levels = 1;
+  L.tile_start[1] = p.total_tiles;
+  render_tc2_kernel<OT, kP, kFromScores, kRing><<<grid, (13 + (kRing ? kTcStageWarps : 0)) * 32, (size_t)p.smem_bytes, st>>>(L);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename OT, bool kFromScores>
+static int launch_tc2(const RenderTcParams& p, cudaStream_t st) {
+  const bool ring = p.nb > 1;
+  switch (p.H * p.W) {
+    case 4096: return ring ? launch_tc2_pr<OT, 4096, kFromScores, true>(p, st) : launch_tc2_pr<OT, 4096, kFromScores, false>(p, st);
+    case 1024: return ring ? launch_tc2_pr<OT, 1024, kFromScores, true>(p, st) : launch_tc2_pr<OT, 1024, kFromScores, false>(p, st);
+    case 256: return ring ? launch_tc2_pr<OT, 256, kFromScores, true>(p, st) : launch_tc2_pr<OT, 256, kFromScores, false>(p, st);
+  }
+  return ring ? launch_tc2_pr<OT, 0, kFromScores, true>(p, st) : launch_tc2_pr<OT, 0, kFromScores, false>(p, st);
+}
+
+// Fill the plan-dependent fields and launch.  p: pointers (and score strides) already set.
+template <bool kFromScores>
+static int run_tc2(RenderTcParams& p, const Tc2Plan& pl, int N, int K, int H, int W, int C, int dtype, cudaStream_t st) {
+  TcPlan base{};
+  base.Kp = pl.Kp; base.c_tile = pl.c_tile; base.nb = pl.nb; base.smem = pl.smem; base.b_slot = pl.b_slot; base.ok = true;
+  if (int rc = fill_tc_units(p, base, N, K, H, W, C, kTc2TilePx)) return rc;
+  p.cw = pl.cw;
+  if (dtype == BLOBSPLAT_BF16) return launch_tc2<__nv_bfloat16, kFromScores>(p, st);
+  return launch_tc2<__half, kFromScores>(p, st);
+}
+
+}  // namespace blobsplat

@@ -2,7 +2,7 @@
 // precomputed score maps.  Replaces splat_features_from_scores (blobctrl/utils/utils.py:57-77; duplicate at
 // blobctrl/pipelines/pipeline_blobnet.py:706-721) when K and C make it a real dense contraction
 // (K >= 12, C >= 64, C % 32 == 0); smaller shapes stay on the FMA engine (feature_splat.cu).
-#include "render_tc.cuh"
+#include "render_tc2.cuh"
 
 namespace blobsplat {
 
@@ -13,6 +13,10 @@ int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_
   if (dtype == BLOBSPLAT_F64) BS_UNSUPPORTED("tensor-core feature splat: float64 runs on the FMA engine");
   RenderTcParams p{};
   p.scores = scores; p.sn = sn; p.sk = sk; p.sp = sp; p.feats = feats; p.grid = out;
+  if (render_tc2_usable(dtype, H, W, nullptr, out, scores, sn, sk, sp)) {        // 16-bit maps: two pixels per lane
+    const Tc2Plan pl2 = plan_tc2(K, C);
+    if (pl2.ok) return run_tc2<true>(p, pl2, N, K, H, W, C, dtype, st);
+  }
   if (int rc = fill_tc_units(p, pl, N, K, H, W, C)) return rc;
   return launch_tc_dtype<true>(p, pl.smem, dtype, st);
 }
