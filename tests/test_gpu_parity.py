@@ -637,6 +637,10 @@ def test_feature_splat_levels_vs_oracle(n, k, levels, dtype, rel):
     (300, 40, 20, 20, 320, torch.bfloat16, 1e-2),    # partial last tile (400 px), 320 channels
     (150, 12, 32, 32, 64, torch.bfloat16, 1e-2),     # 1-2 runs per CTA: single-buffer kernel for comparison
     (37, 127, 12, 12, 32, torch.float32, 1e-5),      # the blob limit of the fused kernel
+    (40, 127, 16, 32, 96, torch.bfloat16, 1e-2),     # two-pixel kernel at the blob limit (Kp = 144, narrow drain sub-steps)
+    (9, 33, 24, 40, 352, torch.bfloat16, 1e-2),      # two-pixel kernel: ragged second channel chunk, partial last tile
+    (64, 32, 64, 64, 320, torch.float16, 2e-3),      # cfg3's level 64 in f16: equal tile ranges, partial runs
+    (6, 16, 30, 31, 64, torch.bfloat16, 1e-2),       # odd width: stays on the one-pixel kernel
     (5, 0, 9, 9, 32, torch.float32, 1e-5)])          # background only
 def test_fused_render_schedules_and_staging_ring(n, m, h, w, c, dtype, rel):
     """blobsplat_render across its schedules (whole runs / equal ranges) and both staging schemes (compute warps with one
