@@ -124,7 +124,14 @@ def ptr(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_of(t: torch.Tensor):
+    """The current CUDA stream of the tensor's device as a raw handle.  torch.cuda.current_stream() builds a Stream
+    object (~8 us per call — a third of a small launch); the raw accessor is the same lookup without it."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(dev_of(t)))
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 

@@ -847,8 +847,12 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   if (total > 0x7fffffffll) BS_UNSUPPORTED("too many tiles for one launch");
   p.total_tiles = (int)total;
   // pick the cheaper partition under the cost model: a tile = 1, staging a unit's operands = BS_STAGE_COST tiles
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  static thread_local int cached_dev = -1, cached_sms = 148;   // host-side launch cost matters for the small launches
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev &&
+      cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+    cached_dev = dev;
+  const int sms = cached_sms;
   const int ctas = std::min(sms, p.total_tiles);
   const int tw = tile_px / kTcTileM;                           // cost of a tile in 128-pixel tiles
   long long ranges = 0;                                        // worst CTA under equal tile ranges
