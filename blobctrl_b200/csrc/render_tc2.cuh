@@ -18,6 +18,9 @@
 #pragma once
 #include "render_tc.cuh"
 
+#ifndef BS_CW_MAX
+#define BS_CW_MAX 128          // widest drain sub-step (channels)
+#endif
 #ifndef BS_PX2
 #define BS_PX2 1               // 16-bit maps: use the two-pixels-per-lane kernel where its preconditions hold
 #endif
@@ -403,7 +406,7 @@ static inline Tc2Plan plan_tc2(int K, int C) {
   // drain sub-step: the widest multiple of 16 channels that divides the tile and leaves room for two 2*cw-column
   // slots next to the two A operands
   int cw = 0;
-  for (int w = 128; w >= 16; w -= 16)
+  for (int w = BS_CW_MAX; w >= 16; w -= 16)
     if (c_tile % w == 0 && 4 * w + pl.Kp <= 512) { cw = w; break; }
   if (cw == 0) return pl;
   pl.c_tile = c_tile; pl.cw = cw;
