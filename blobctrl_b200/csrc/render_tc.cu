@@ -4,7 +4,7 @@
 
 namespace blobsplat {
 
-void render_tc_limits(int* max_k, int* c_multiple, int* max_c) { *max_k = kTcMaxBlobs + 1; *c_multiple = 32; *max_c = 1 << 20; }
+void render_tc_limits(int* max_k, int* c_multiple, int* max_c) { *max_k = kTcMaxBlobs + 1; *c_multiple = 1; *max_c = 1 << 20; }
 
 int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why) {
   *why = "";

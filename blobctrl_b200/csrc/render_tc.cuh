@@ -817,11 +817,11 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
   const int kstep = tf32 ? 8 : 16;
   pl.Kp = round_up(K + kTcKOff, kstep);
   if (K - 1 > kTcMaxBlobs) { pl.why = "more than 127 blobs: use the FMA engine"; return pl; }
-  if (C % 32 != 0) { pl.why = "C must be a multiple of 32 for the tensor-core render"; return pl; }
+  if (C < 1) { pl.why = "no channels"; return pl; }
   const int a_cols = tf32 ? 2 * pl.Kp : pl.Kp / 2;
   const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : 2);                  // B bytes per channel (hi+lo fp32 | 16-bit)
   const size_t fixed = (size_t)(pl.Kp + 4) * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
-  int c_tile = std::min(kTcMaxCTile, C);
+  int c_tile = std::min(kTcMaxCTile, round_up(C, 32));     // any C: the last chunk may be ragged (zero B columns, predicated drain)
   c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
   if (c_tile < 32) { pl.why = "K too large for shared/tensor memory"; return pl; }

@@ -393,13 +393,13 @@ struct Tc2Plan { int Kp, c_tile, cw, nb; size_t smem, b_slot; bool ok; };
 static inline Tc2Plan plan_tc2(int K, int C) {
   Tc2Plan pl{};
   pl.ok = false;
-  if (K - 1 > kTcMaxBlobs || C % 32 != 0) return pl;
+  if (K - 1 > kTcMaxBlobs || C < 1) return pl;
   pl.Kp = round_up(K + kTcKOff, 16);
   const size_t fixed = (size_t)2 * (pl.Kp + 4) * kTcTileM * 4 + 2 * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) +
                        sizeof(TcBarriers) + 512;
   const size_t per_c = (size_t)pl.Kp * 2;
   if (fixed + per_c * 32 > kTcSmemBudget) return pl;
-  int c_tile = std::min(kTcMaxCTile, C);
+  int c_tile = std::min(kTcMaxCTile, round_up(C, 32));
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
   for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
     if (C % c == 0) { c_tile = c; break; }

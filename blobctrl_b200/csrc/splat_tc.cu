@@ -1,7 +1,7 @@
 // Stand-alone stage 3 on tensor cores — instantiations of render_tc.cuh with the A operand loaded from
 // precomputed score maps.  Replaces splat_features_from_scores (blobctrl/utils/utils.py:57-77; duplicate at
 // blobctrl/pipelines/pipeline_blobnet.py:706-721) when K and C make it a real dense contraction
-// (K >= 12, C >= 64, C % 32 == 0); smaller shapes stay on the FMA engine (feature_splat.cu).
+// (K >= 12, C >= 64); smaller shapes stay on the FMA engine (feature_splat.cu).
 #include "render_tc2.cuh"
 
 namespace blobsplat {

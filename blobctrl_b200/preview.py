@@ -52,7 +52,7 @@ class GraphedBlobRenderer:
         with torch.cuda.stream(self.stream):
             c = self.feats.shape[-1] if self.feats is not None else 0
             self.grid = None
-            if self.feats is not None and c % 32 == 0 and c >= 64:
+            if self.feats is not None and c >= 64:
                 try:
                     self.scores, self.grid = ops.render_fused(self.xs, self.ys, self.covs, self.sizes, self.feats, self.h, self.w)
                     return

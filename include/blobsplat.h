@@ -80,7 +80,7 @@ typedef struct {
   int sm_arch;            /* 100 */
   int max_blobs;          /* largest M accepted by blobsplat_scores */
   int tensor_max_k;       /* largest K = M+1 the tensor-core render accepts */
-  int tensor_c_multiple;  /* C must be a multiple of this for the tensor-core render */
+  int tensor_c_multiple;  /* C must be a multiple of this for the tensor-core render (1: any C) */
   int tensor_max_c;       /* largest C the tensor-core render accepts */
 } blobsplat_caps;
 
@@ -153,7 +153,7 @@ BLOBSPLAT_API int blobsplat_pyramid(const void* in, void* const* outs, int n_lev
  *           ([N,K,H,W] contiguous: K*P, P, 1;  [N,H,W,K] contiguous: P*K, 1, K)
  *   features [N, K, C] contiguous, same dtype as scores and out.
  *   engine: AUTO runs the contraction on tcgen05 tensor cores when it is a real dense one (K >= 12, C >= 64,
- *           C % 32 == 0, K <= 128, not float64; float32 uses the 3xTF32 split) and on CUDA-core FMA tiles
+ *           K <= 128, not float64; float32 uses the 3xTF32 split) and on CUDA-core FMA tiles
  *           otherwise; FMA / TENSOR force one (TENSOR fails with BLOBSPLAT_E_UNSUPPORTED outside its envelope).
  */
 BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride_k, int64_t stride_p,
@@ -166,7 +166,7 @@ BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, 
  *      `for s in sizes: splat_features_from_scores(scores_pyramid[s], features[s], s)` over the pyramid returned by
  *      splat_features (utils.py:235-241, 57-77).  All arrays are HOST arrays of n_levels entries (pointers are
  *      device pointers).  engine AUTO / FMA: level by level exactly as (3).  engine TENSOR: when every level is
- *      a dense contraction with the same operand tiling (2..4 levels, C[i] >= 64 and C[i] % 32 == 0 with one
+ *      a dense contraction with the same operand tiling (2..4 levels, C[i] >= 64 with one
  *      common channel tile) the levels run as ONE tcgen05 launch over the concatenated tile sequence, otherwise
  *      level by level on the tensor engine.
  */

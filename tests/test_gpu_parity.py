@@ -348,9 +348,14 @@ def test_tensor_engine_rejects_outside_envelope():
     U = _impl()
     from blobctrl_b200 import _capi
     sc = torch.rand(1, 5, 8, 8, device=DEV); ft = torch.randn(1, 5, 30, device=DEV)
-    with pytest.raises(_capi.BlobSplatError):                           # C % 32 != 0
-        U.splat_features_from_scores(sc, ft, 8, channels_last=False, engine="tensor")
-    out = U.splat_features_from_scores(sc, ft, 8, channels_last=False)  # auto -> FMA
+    with pytest.raises(_capi.BlobSplatError):                           # float64 stays on the FMA engine
+        U.splat_features_from_scores(sc.double(), ft.double(), 8, channels_last=False, engine="tensor")
+    big = torch.rand(1, 130, 8, 8, device=DEV)
+    with pytest.raises(_capi.BlobSplatError):                           # more than 128 planes
+        U.splat_features_from_scores(big, torch.randn(1, 130, 64, device=DEV), 8, channels_last=False, engine="tensor")
+    forced = U.splat_features_from_scores(sc, ft, 8, channels_last=False, engine="tensor")   # any C: ragged channel tile
+    out = U.splat_features_from_scores(sc, ft, 8, channels_last=False)  # auto -> FMA (tiny K, C)
+    assert (forced - out).abs().max().item() <= 2e-5 * out.abs().max().item()
     want = torch.einsum("nkhw,nkc->nchw", sc, ft)
     assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item()
 
@@ -641,6 +646,9 @@ def test_feature_splat_levels_vs_oracle(n, k, levels, dtype, rel):
     (9, 33, 24, 40, 352, torch.bfloat16, 1e-2),      # two-pixel kernel: ragged second channel chunk, partial last tile
     (64, 32, 64, 64, 320, torch.float16, 2e-3),      # cfg3's level 64 in f16: equal tile ranges, partial runs
     (6, 16, 30, 31, 64, torch.bfloat16, 1e-2),       # odd width: stays on the one-pixel kernel
+    (5, 20, 16, 16, 100, torch.float32, 1e-5),       # channel count off the 32-grid: ragged tile, scalar feature loads
+    (3, 33, 32, 32, 1029, torch.bfloat16, 1e-2),     # 1029 channels: four chunks, the last one 69 wide
+    (4, 12, 20, 24, 67, torch.float16, 2e-3),
     (5, 0, 9, 9, 32, torch.float32, 1e-5)])          # background only
 def test_fused_render_schedules_and_staging_ring(n, m, h, w, c, dtype, rel):
     """blobsplat_render across its schedules (whole runs / equal ranges) and both staging schemes (compute warps with one
