@@ -52,25 +52,54 @@ pyramid_kernel(const T* __restrict__ in, PyramidPtrs outs, int B, int S) {
   const size_t b = i / ((size_t)bs * bs);
   A v[E][E];
   const T* src = in + b * (size_t)S * S + (size_t)by * E * S + (size_t)bx * E;
+  // a block row is E contiguous elements: 16-byte loads where that is a whole number of vectors and aligned
+  constexpr int VL = 16 / sizeof(T);
+  const bool vec = (E % VL == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && (S % VL == 0);
+  if (vec) {
 #pragma unroll
-  for (int r = 0; r < E; ++r)
+    for (int r = 0; r < E; ++r)
 #pragma unroll
-    for (int c = 0; c < E; ++c) v[r][c] = (A)Cvt<T>::to(src[(size_t)r * S + c]);
+      for (int c0 = 0; c0 < E; c0 += VL) {
+        if constexpr (E % VL == 0) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * S + c0));
+          const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+          for (int j = 0; j < VL; ++j) v[r][c0 + j] = (A)Cvt<T>::to(e[j]);
+        }
+      }
+  } else {
+#pragma unroll
+    for (int r = 0; r < E; ++r)
+#pragma unroll
+      for (int c = 0; c < E; ++c) v[r][c] = (A)Cvt<T>::to(src[(size_t)r * S + c]);
+  }
 #pragma unroll
   for (int l = 1; l <= L; ++l) {
     const int e = E >> l;   // block edge at this level
     const int s = S >> l;   // image size at this level
     T* dst = (T*)outs.p[l - 1] + b * (size_t)s * s + (size_t)by * e * s + (size_t)bx * e;
 #pragma unroll
-    for (int r = 0; r < e; ++r)
+    for (int r = 0; r < e; ++r) {
+      T q[E];
 #pragma unroll
       for (int c = 0; c < e; ++c) {
         const A top = (A)0.5 * v[2 * r][2 * c] + (A)0.5 * v[2 * r][2 * c + 1];
         const A bot = (A)0.5 * v[2 * r + 1][2 * c] + (A)0.5 * v[2 * r + 1][2 * c + 1];
-        const T q = Cvt<T>::from((A)0.5 * top + (A)0.5 * bot);
-        dst[(size_t)r * s + c] = q;
-        v[r][c] = (A)Cvt<T>::to(q);
+        q[c] = Cvt<T>::from((A)0.5 * top + (A)0.5 * bot);
+        v[r][c] = (A)Cvt<T>::to(q[c]);
       }
+      // one store per block row where its e elements make an aligned 4 / 8 / 16-byte word
+      T* drow = dst + (size_t)r * s;
+      const int bytes = e * (int)sizeof(T);
+      const bool al = (reinterpret_cast<uintptr_t>(outs.p[l - 1]) & 15) == 0 && (s * (int)sizeof(T)) % bytes == 0;
+      if (al && bytes == 16) *reinterpret_cast<uint4*>(drow) = *reinterpret_cast<const uint4*>(q);
+      else if (al && bytes == 8) *reinterpret_cast<uint2*>(drow) = *reinterpret_cast<const uint2*>(q);
+      else if (al && bytes == 4) *reinterpret_cast<uint32_t*>(drow) = *reinterpret_cast<const uint32_t*>(q);
+      else {
+#pragma unroll
+        for (int c = 0; c < e; ++c) drow[c] = q[c];
+      }
+    }
   }
 }
 
