@@ -12,14 +12,16 @@
 
 namespace blobsplat {
 
-template <typename T>
+// V = pixels per thread: 4, or 8 for 16-bit dtypes when w % 8 == 0 (16-byte loads and stores)
+template <typename T, int V>
 __global__ void __launch_bounds__(256)
 conditioning_fill_kernel(const T* __restrict__ scores, const T* __restrict__ feats, T* __restrict__ out, int K, int C,
                          int h, int w, int c_total, int c_off, int halves, bool write_scores) {
   // out[b, c_off + j, y, x + half*w]:  j < K_s (score planes, when write_scores) then C feature planes
   const int b = blockIdx.z;
   const int planes = (write_scores ? K : 0) + C;
-  const int P = h * w, w4 = w >> 2;
+  const int P = h * w, w4 = w / V;
+  const bool vec_in = (reinterpret_cast<uintptr_t>(scores) & 15) == 0;    // rows are V-aligned (w % V == 0)
   const int items_per_plane = h * w4;
   const long long total = (long long)planes * items_per_plane;
   const int Wt = w * halves;
@@ -28,39 +30,51 @@ conditioning_fill_kernel(const T* __restrict__ scores, const T* __restrict__ fea
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int plane = (int)(i / items_per_plane);
     const int r = (int)(i - (long long)plane * items_per_plane);
-    const int y = r / w4, x = (r - y * w4) << 2;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (write_scores && plane < K) {
+    const int y = r / w4, x = (r - y * w4) * V;
+    using VecT = typename std::conditional<sizeof(T) * V == 16, uint4, uint2>::type;   // V pixels of T
+    float v[V];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = (float)Cvt<T>::to(sb[(size_t)plane * P + y * w + x + j]);
-    } else {
-      const int c = plane - (write_scores ? K : 0);
-      for (int k = 0; k < K; ++k) {
-        const float f = (float)Cvt<T>::to(fb[(size_t)k * C + c]);
+    for (int j = 0; j < V; ++j) v[j] = 0.f;
+    const bool is_score = write_scores && plane < K;
+    const int c = plane - (write_scores ? K : 0);
+    for (int k = is_score ? plane : 0; k < (is_score ? plane + 1 : K); ++k) {
+      const float f = is_score ? 1.0f : (float)Cvt<T>::to(fb[(size_t)k * C + c]);
+      const T* sp = sb + (size_t)k * P + y * w + x;      // V adjacent pixels of score plane k
+      T px[V];
+      if (vec_in) {
+        *reinterpret_cast<VecT*>(px) = __ldg(reinterpret_cast<const VecT*>(sp));
+      } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = fmaf((float)Cvt<T>::to(sb[(size_t)k * P + y * w + x + j]), f, v[j]);
+        for (int j = 0; j < V; ++j) px[j] = sp[j];
       }
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = is_score ? (float)Cvt<T>::to(px[j]) : fmaf((float)Cvt<T>::to(px[j]), f, v[j]);
     }
     T* o = out + (((size_t)b * c_total + c_off + plane) * h + y) * Wt + x;
-    for (int hf = 0; hf < halves; ++hf) {
-      if constexpr (sizeof(T) == 4) {
-        *reinterpret_cast<float4*>(o + hf * w) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-        T t[4] = {Cvt<T>::from(v[0]), Cvt<T>::from(v[1]), Cvt<T>::from(v[2]), Cvt<T>::from(v[3])};
-        *reinterpret_cast<uint2*>(o + hf * w) = *reinterpret_cast<const uint2*>(t);
-      }
-    }
+    T t[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) t[j] = Cvt<T>::from(v[j]);
+    for (int hf = 0; hf < halves; ++hf) *reinterpret_cast<VecT*>(o + hf * w) = *reinterpret_cast<const VecT*>(t);
   }
 }
 
 template <typename T>
 static int launch_fill(const void* scores, const void* feats, void* out, int B, int K, int C, int h, int w, int c_total,
                        int c_off, int halves, bool write_scores, cudaStream_t st) {
-  const long long total = (long long)((write_scores ? K : 0) + C) * h * (w >> 2);
+  // scores rows must be aligned to the vector: capi checks w % 4 == 0 and a 16-byte aligned output
+  const bool wide = sizeof(T) == 2 && (w % 8) == 0;
+  const int V = wide ? 8 : 4;
+  const long long total = (long long)((write_scores ? K : 0) + C) * h * (w / V);
   const unsigned bx = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
   dim3 grid(bx, 1, (unsigned)B);
-  conditioning_fill_kernel<T><<<grid, 256, 0, st>>>((const T*)scores, (const T*)feats, (T*)out, K, C, h, w, c_total, c_off,
-                                                   halves, write_scores);
+  if (wide) {
+    if constexpr (sizeof(T) == 2)
+      conditioning_fill_kernel<T, 8><<<grid, 256, 0, st>>>((const T*)scores, (const T*)feats, (T*)out, K, C, h, w, c_total,
+                                                          c_off, halves, write_scores);
+  } else {
+    conditioning_fill_kernel<T, 4><<<grid, 256, 0, st>>>((const T*)scores, (const T*)feats, (T*)out, K, C, h, w, c_total,
+                                                        c_off, halves, write_scores);
+  }
   BS_CUDA(cudaGetLastError());
   return 0;
 }
