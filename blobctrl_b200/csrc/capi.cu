@@ -169,9 +169,11 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
   const char* why = nullptr;
   const bool tc_ok = dtype != BLOBSPLAT_F64 && render_tc_supported(K, C, H, W, dtype, dtype, &why);
   if (engine == BLOBSPLAT_ENGINE_TENSOR && !tc_ok) BS_UNSUPPORTED("tensor-core feature splat: %s", why ? why : "float64");
-  // AUTO: tensor engine for a real contraction (K >= 12) and, whatever K, for outputs large enough that its streaming
-  // drain beats the FMA tiles (>= 16 M elements: 2.7x at the pipeline's K = 1, C = 1024 splat of 16 images)
-  const bool big = (long long)N * C * H * W >= (1ll << 24);
+  // AUTO: tensor engine for a real contraction (K >= 12) and, for 16-bit maps, whatever K once the output is large
+  // enough that its streaming drain beats the FMA tiles (>= 16 M elements: 2.7x at the pipeline's K = 1, C = 1024
+  // splat of 16 images; 16-bit products are exact in the fp32 accumulator, so K = 1 stays bit-identical).  float32
+  // keeps small K on the FMA engine: a single product is exact there, 3xTF32 is not.
+  const bool big = dtype != BLOBSPLAT_F32 && (long long)N * C * H * W >= (1ll << 24);
   if (tc_ok && (engine == BLOBSPLAT_ENGINE_TENSOR || (engine == BLOBSPLAT_ENGINE_AUTO && C >= 64 && (K >= 12 || big))))
     return feature_splat_tc_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
                                      (cudaStream_t)stream);

@@ -153,7 +153,7 @@ BLOBSPLAT_API int blobsplat_pyramid(const void* in, void* const* outs, int n_lev
  *           ([N,K,H,W] contiguous: K*P, P, 1;  [N,H,W,K] contiguous: P*K, 1, K)
  *   features [N, K, C] contiguous, same dtype as scores and out.
  *   engine: AUTO runs the contraction on tcgen05 tensor cores when it is a real dense one (C >= 64 and K >= 12, or
- *           any K once the output has >= 2^24 elements;
+ *           for 16-bit maps any K once the output has >= 2^24 elements;
  *           K <= 128, not float64; float32 uses the 3xTF32 split) and on CUDA-core FMA tiles
  *           otherwise; FMA / TENSOR force one (TENSOR fails with BLOBSPLAT_E_UNSUPPORTED outside its envelope).
  */
