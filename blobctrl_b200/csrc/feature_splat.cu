@@ -52,8 +52,9 @@ feature_splat_fma(const T* __restrict__ scores, long long sn, long long sk, long
       f_s[kk][cc] = (k < K && c < C) ? (A)Cvt<T>::to(fbase[(size_t)k * C + c]) : (A)0;
     }
     __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kFsKC; ++kk) {
+    const int kcnt = min(kFsKC, K - k0);      // small K (the pipeline's K = 1 splat): no work on the zero padding
+#pragma unroll 4
+    for (int kk = 0; kk < kcnt; ++kk) {
       A wv[PX], fv[8];
 #pragma unroll
       for (int j = 0; j < PX; ++j) wv[j] = w_s[kk][lane * PX + j];
