@@ -377,6 +377,25 @@ def test_host_renderer_chunked_copy_matches_single_call():
         assert torch.equal(out["feature_grid"], ref["feature_grid"])
 
 
+def test_host_renderer_back_to_back_calls_do_not_mix_inputs():
+    """Double-buffered input staging: consecutive calls with different host inputs (copies of call i+1 overlap the renders
+    of call i) each return their own result; outputs are snapshotted in stream order before the next call overwrites them."""
+    from blobctrl_b200.streaming import HostRenderer
+    U = _impl()
+    n, m, s, c = 24, 9, 32, 64
+    r = HostRenderer(n, m, s, c, torch.float32, DEV, chunks=3)
+    sets = [blob_oracle.synthetic_blobs(n, m, seed=40 + i, c=c) for i in range(5)]
+    hosts = [{k: torch.from_numpy(v).pin_memory() for k, v in syn.items()} for syn in sets]
+    snaps = []
+    for h in hosts:                                     # no synchronisation between the calls
+        out = r(h["xs"], h["ys"], h["covs"], h["sizes"], h["features"])
+        snaps.append((out["scores_pyramid"][s].clone(), out["feature_grid"].clone()))
+    torch.cuda.synchronize()
+    for syn, (d, g) in zip(sets, snaps):
+        ref = U.splat_features(**_blob(syn), features=_cuda(syn["features"]), score_size=s, interp_size=s, ret_layout=False)
+        assert torch.equal(d, ref["scores_pyramid"][s]) and torch.equal(g, ref["feature_grid"])
+
+
 def test_ellipse_front_end_matches_script_recipe():
     """blobsplat_scores_ellipse (N3): all 40 demo ellipses as one batch == the reference's host recipe + renderer
     (golden fp64 maps), including the two degenerate 1e-5-pixel ellipses (exactly one pixel at 1.0)."""
