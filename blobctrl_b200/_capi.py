@@ -52,6 +52,7 @@ SIGNATURES = {
     "blobsplat_conditioning_fill": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_residual_inject": [_P, _P, _P, ctypes.c_float, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_render": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "blobsplat_render_multiscale": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P],
 }
 
 _lib: Optional[ctypes.CDLL] = None

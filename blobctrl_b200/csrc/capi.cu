@@ -264,4 +264,36 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
                             (cudaStream_t)stream);
 }
 
+int blobsplat_render_multiscale(const float* xs, const float* ys, const float* covs, const float* sizes, int N, int M,
+                                int S, int n_levels, const void* const* features, const int* C, void* const* composed,
+                                void* const* grids, int dtype, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && S >= 1, "bad shape N=%d M=%d S=%d", N, M, S);
+  BS_CHECK_ARG(n_levels >= 1 && n_levels <= 4, "1..4 levels per call (got %d)", n_levels);
+  BS_CHECK_ARG((S % (1 << (n_levels - 1))) == 0, "S=%d is not divisible by 2^%d", S, n_levels - 1);
+  BS_CHECK_ARG(valid_dtype(dtype) && dtype != BLOBSPLAT_F64, "float32 / bfloat16 / float16 maps only");
+  BS_CHECK_ARG(features && C && composed && grids, "NULL level array");
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(features[0] && grids[0] && composed[0], "level 0 needs features, a grid and a composed-map buffer");
+  for (int l = 1; l < n_levels; ++l) BS_CHECK_ARG(composed[l] != nullptr, "level %d composed-map buffer is NULL", l);
+  // level 0: stages 1+2+3 fused; levels 1..: exact 2x2 means of the composed maps, then stage 3 per level
+  int rc = blobsplat_render(xs, ys, covs, sizes, features[0], dtype, N, M, S, S, C[0], composed[0], grids[0], dtype, device,
+                            stream);
+  if (rc != BLOBSPLAT_OK || n_levels == 1) return rc;
+  rc = blobsplat_pyramid(composed[0], composed + 1, n_levels - 1, N * (M + 1), S, dtype, device, stream);
+  if (rc != BLOBSPLAT_OK) return rc;
+  const void* sc[4]; const void* ft[4]; void* out[4];
+  int64_t sn[4], sk[4], sp[4];
+  int Cs[4], Hs[4], Ws[4], n = 0;
+  for (int l = 1; l < n_levels; ++l) {
+    if (!features[l]) continue;                         // level wanted as maps only
+    BS_CHECK_ARG(grids[l] != nullptr, "level %d has features but no grid buffer", l);
+    const int s = S >> l;
+    sc[n] = composed[l]; ft[n] = features[l]; out[n] = grids[l];
+    sn[n] = (int64_t)(M + 1) * s * s; sk[n] = (int64_t)s * s; sp[n] = 1;
+    Cs[n] = C[l]; Hs[n] = s; Ws[n] = s; ++n;
+  }
+  return blobsplat_feature_splat_levels(n, sc, sn, sk, sp, ft, out, N, M + 1, Cs, Hs, Ws, dtype, BLOBSPLAT_ENGINE_AUTO, device,
+                                        stream);
+}
+
 }  // extern "C"

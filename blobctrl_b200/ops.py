@@ -231,6 +231,34 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
     return composed, grid
 
 
+def render_multiscale(xs, ys, covs, sizes, size: int, level_features: Sequence[Optional[torch.Tensor]],
+                      out_dtype: torch.dtype):
+    """blobsplat_render_multiscale: level l has size ``size >> l``; level_features[l] is [N, M+1, C_l] or None (maps only).
+    Returns (composed maps per level, grids per level (None where no features)).  One C call for the whole pyramid."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    if covs_c.dtype != torch.float32:
+        raise C.BlobSplatError("blobsplat: unsupported: fused render takes float32 blob parameters")
+    dev = covs_c.device
+    L = len(level_features)
+    feats, comps, grids, cs = [], [], [], []
+    for l, f in enumerate(level_features):
+        s = size >> l
+        comps.append(C.new_output((n, m + 1, s, s), out_dtype, dev))
+        if f is None:
+            feats.append(None); grids.append(None); cs.append(0)
+            continue
+        f = f.to(device=dev, dtype=out_dtype).contiguous()
+        if f.ndim != 3 or f.shape[0] != n or f.shape[1] != m + 1:
+            raise RuntimeError(f"features must be [N, M+1, C] = [{n}, {m + 1}, C], got {tuple(f.shape)}")
+        feats.append(f); cs.append(f.shape[2])
+        grids.append(C.new_output((n, f.shape[2], s, s), out_dtype, dev))
+    vp = lambda ts: (ctypes.c_void_p * L)(*[None if t is None else t.data_ptr() for t in ts])
+    C.check(C.lib().blobsplat_render_multiscale(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), n, m, size, L, vp(feats),
+                                                (ctypes.c_int * L)(*cs), vp(comps), vp(grids), C.dtype_code(out_dtype),
+                                                C.dev_of(covs_c), C.stream_of(covs_c)))
+    return comps, grids
+
+
 def render_fused_into(xs, ys, covs, sizes, features, height: int, width: int, composed: Optional[torch.Tensor],
                       grid: torch.Tensor) -> None:
     """blobsplat_render into caller-owned (contiguous) output buffers; inputs must already be dense float32 [N,M]

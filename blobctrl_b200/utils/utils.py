@@ -223,6 +223,22 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
     """
     if not level_features:
         raise ValueError("level_features is empty")
+    # the common shape — consecutive halvings from score_size down, features at the top level, 16/32-bit maps — is one
+    # C call (blobsplat_render_multiscale): at small batches the per-call host overhead bounds the multi-call path
+    top_f = level_features.get(score_size)
+    n_lv = 1
+    while (score_size >> n_lv) >= min(level_features) and (score_size % (1 << n_lv)) == 0:
+        n_lv += 1
+    dt = out_dtype or covs.dtype
+    if (engine == "auto" and top_f is not None and n_lv <= 4 and covs.dtype != torch.float64 and dt != torch.float64
+            and all(s in [score_size >> l for l in range(n_lv)] for s in level_features)):
+        try:
+            comps, gl = ops.render_multiscale(xs, ys, covs, sizes, score_size,
+                                              [level_features.get(score_size >> l) for l in range(n_lv)], dt)
+            return {"scores_pyramid": {score_size >> l: comps[l] for l in range(n_lv)},
+                    "feature_grids": {score_size >> l: gl[l] for l in range(n_lv) if gl[l] is not None}}
+        except C.BlobSplatError:
+            pass                                     # outside the fused render's envelope: the general path below
     grids = {}
     d = None
     top = level_features.get(score_size)

@@ -216,6 +216,19 @@ BLOBSPLAT_API int blobsplat_render(const float* xs, const float* ys, const float
                      const void* features, int feat_dtype, int N, int M, int H, int W, int C,
                      void* composed, void* grid, int out_dtype, int device, void* stream);
 
+/*
+ * (4b) the multi-resolution conditioning in ONE call (BASELINE configs[2]): level l has size S >> l.  Level 0 is (4);
+ *      levels 1.. are pyramid_resize of its composed maps (utils.py:280-294, exact 2x2 means) followed by
+ *      splat_features_from_scores per level (utils.py:57-77).  HOST arrays of n_levels (1..4) entries:
+ *      features[l] [N, M+1, C[l]] (NULL = level wanted as maps only), composed[l] [N, M+1, S>>l, S>>l] (required: the
+ *      pyramid is an output, utils.py:235-241), grids[l] [N, C[l], S>>l, S>>l].  float32 parameters; float32 /
+ *      bfloat16 / float16 features and maps of one dtype.  Same launches as calling (4), (2b), (3b) in sequence — it
+ *      exists because at small batches the host's per-call overhead, not the GPU, bounds that sequence.
+ */
+BLOBSPLAT_API int blobsplat_render_multiscale(const float* xs, const float* ys, const float* covs, const float* sizes,
+                              int N, int M, int S, int n_levels, const void* const* features, const int* C,
+                              void* const* composed, void* const* grids, int dtype, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

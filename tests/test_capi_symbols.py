@@ -24,7 +24,7 @@ def test_header_declares_the_expected_entry_points():
     d = _declared()
     assert set(d) == {"blobsplat_abi_version", "blobsplat_get_caps", "blobsplat_last_error", "blobsplat_scores",
                       "blobsplat_scores_ellipse", "blobsplat_composite", "blobsplat_resize_bilinear", "blobsplat_pyramid",
-                      "blobsplat_feature_splat", "blobsplat_feature_splat_levels", "blobsplat_conditioning_fill", "blobsplat_residual_inject", "blobsplat_render"}
+                      "blobsplat_feature_splat", "blobsplat_feature_splat_levels", "blobsplat_conditioning_fill", "blobsplat_residual_inject", "blobsplat_render", "blobsplat_render_multiscale"}
 
 
 def test_library_exports_every_declared_symbol():

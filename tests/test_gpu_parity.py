@@ -696,3 +696,23 @@ def test_fused_render_schedules_and_staging_ring(n, m, h, w, c, dtype, rel):
     want_g2 = blob_oracle.splat_features_from_scores(_np(comp).astype(np.float64), _np(feats).astype(np.float64), None,
                                                      channels_last=False)
     close_scaled(_np(g2), want_g2, 2 * rel, f"stage 3 from maps N={n} M={m} C={c}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_render_multiscale_one_call_equals_the_call_sequence(dtype):
+    """blobsplat_render_multiscale == blobsplat_render + blobsplat_pyramid + blobsplat_feature_splat_levels, bit for bit,
+    including a level that is wanted as maps only."""
+    from blobctrl_b200 import ops
+    n, m, s = 5, 20, 32
+    syn = blob_oracle.synthetic_blobs(n, m, seed=77, c=1)
+    b = _blob(syn)
+    g = torch.Generator().manual_seed(3)
+    feats = [torch.randn(n, m + 1, c, generator=g).to(DEV).to(dtype) if c else None for c in (64, 0, 160, 96)]
+    comps, grids = ops.render_multiscale(b["xs"], b["ys"], b["covs"], b["sizes"], s, feats, dtype)
+    d0, g0 = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats[0], s, s, out_dtype=dtype)
+    pyr = ops.halving_pyramid(d0, s >> 3)
+    assert torch.equal(comps[0], d0) and torch.equal(grids[0], g0) and grids[1] is None
+    for l in range(1, 4):
+        assert torch.equal(comps[l], pyr[s >> l])
+        if feats[l] is not None:
+            assert torch.equal(grids[l], ops.feature_splat(pyr[s >> l], feats[l]))
