@@ -166,7 +166,9 @@ def workload_config(n_gpus):
     return {"workload": f"cfg5b: {N_IMG} images/GPU x {M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS} feature grid, fp32 "
                         f"(BASELINE.json configs[4]; largest single-GPU config)",
             "images_per_gpu": N_IMG, "blobs": M_BLOBS, "size": SIZE, "channels": CHANNELS, "sharding": f"by-image x{n_gpus}",
-            "l2": "outputs 6.5 GB/step stream through the 126 MB L2 (>> L2); the 87 MB of inputs are re-read each step"}
+            "l2": "outputs 6.5 GB/step stream through the 126 MB L2 (>> L2); the 87 MB of inputs are re-read each step",
+            "e2e_pipeline": "HostRenderer: pinned H2D in 4 chunks on a copy stream, double-buffered staging (the copies of "
+                            "step i+1 overlap the renders of step i), D2H of the last image's maps every step"}
 
 
 # ----------------------------------------------------------------------------------------------------
