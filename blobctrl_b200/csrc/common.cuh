@@ -1,5 +1,6 @@
 // Shared device/host helpers for the blob-splat kernels (sm_100a only).
 #pragma once
+#include <utility>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -139,6 +140,36 @@ template <> struct VecStore<__half, 1> {
 
 // number of elements in one 128-bit store
 template <typename T> struct Vec128 { static constexpr int n = 16 / sizeof(T); };
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------
+// Kernels launched with launch_pdl may begin (block scheduling, TMEM / barrier set-up) while the previous kernel in
+// the stream is still draining; they call pdl_wait() before their first global-memory access, which blocks until
+// every prerequisite grid has completed and its writes are visible.  pdl_launch_dependents() lets the NEXT kernel's
+// blocks be scheduled as soon as this grid's blocks start to retire.  Saves the launch gap between the back-to-back
+// launches of a multi-resolution render (BS_PDL=0 turns it off).
+#ifndef BS_PDL
+#define BS_PDL 1
+#endif
+__device__ __forceinline__ void pdl_wait() {
+#if BS_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if BS_PDL
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = BS_PDL;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr float kLog2e = 1.4426950408889634f;
 

@@ -417,6 +417,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
   if (threadIdx.x == 0) TC_STAMP(1);
+  pdl_launch_dependents();
+  pdl_wait();                                      // set-up above overlapped the previous kernel's tail
   const uint32_t tmem_a = tmem + (uint32_t)p0.c_tile;             // A hi; A lo follows at + Kp/kACols columns
   const int a_cols = p0.Kp / kACols;
 
@@ -896,9 +898,8 @@ static int launch_tc_pr(const RenderTcParams& p, cudaStream_t st) {
   L.lv[0].pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
   L.n_levels = 1;
   L.tile_start[1] = p.total_tiles;
-  render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>
-      <<<grid, (4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32, (size_t)p.smem_bytes, st>>>(L);
-  BS_CUDA(cudaGetLastError());
+  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>, dim3(grid),
+                     dim3((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32), (size_t)p.smem_bytes, st, L));
   return 0;
 }
 

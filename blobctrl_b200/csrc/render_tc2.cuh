@@ -115,6 +115,8 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  pdl_launch_dependents();
+  pdl_wait();                                            // set-up above overlapped the previous kernel's tail
   const uint32_t tmem_a = tmem + (uint32_t)(4 * cw);     // A even; A odd follows at + a_cols
   const int a_cols = p.Kp / 2;                           // two k per 32-bit column
 
@@ -442,8 +444,8 @@ static int launch_tc2_pr(const RenderTcParams& p, cudaStream_t st) {
   L.lv[0] = p;
   L.n_levels = 1;
   L.tile_start[1] = p.total_tiles;
-  render_tc2_kernel<OT, kP, kFromScores, kRing><<<grid, (13 + (kRing ? kTcStageWarps : 0)) * 32, (size_t)p.smem_bytes, st>>>(L);
-  BS_CUDA(cudaGetLastError());
+  BS_CUDA(launch_pdl(render_tc2_kernel<OT, kP, kFromScores, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
+                     (size_t)p.smem_bytes, st, L));
   return 0;
 }
 

@@ -47,6 +47,8 @@ pyramid_kernel(const T* __restrict__ in, PyramidPtrs outs, int B, int S) {
   const int bs = S / E;      // blocks per row
   const size_t total = (size_t)B * bs * bs;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (i >= total) return;
   const int bx = (int)(i % bs), by = (int)((i / bs) % bs);
   const size_t b = i / ((size_t)bs * bs);
@@ -131,11 +133,10 @@ static int launch_pyramid(const void* in, void* const* outs, int n_levels, int B
   const size_t total = (size_t)B * (S >> n_levels) * (S >> n_levels);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   switch (n_levels) {
-    case 1: pyramid_kernel<T, A, 1><<<blocks, 256, 0, st>>>((const T*)in, p, B, S); break;
-    case 2: pyramid_kernel<T, A, 2><<<blocks, 256, 0, st>>>((const T*)in, p, B, S); break;
-    case 3: pyramid_kernel<T, A, 3><<<blocks, 256, 0, st>>>((const T*)in, p, B, S); break;
+    case 1: BS_CUDA(launch_pdl(pyramid_kernel<T, A, 1>, dim3(blocks), dim3(256), 0, st, (const T*)in, p, B, S)); break;
+    case 2: BS_CUDA(launch_pdl(pyramid_kernel<T, A, 2>, dim3(blocks), dim3(256), 0, st, (const T*)in, p, B, S)); break;
+    case 3: BS_CUDA(launch_pdl(pyramid_kernel<T, A, 3>, dim3(blocks), dim3(256), 0, st, (const T*)in, p, B, S)); break;
   }
-  BS_CUDA(cudaGetLastError());
   return 0;
 }
 

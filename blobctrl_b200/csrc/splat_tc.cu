@@ -42,8 +42,8 @@ static int launch_tc_levels_r(RenderTcLevels& L, size_t smem, cudaStream_t st) {
   L.tile_start[L.n_levels] = (int)total;
   if (total == 0) return 0;
   const int grid = (int)std::min<long long>(sm_count, total);
-  render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing><<<grid, (13 + (kRing ? kTcStageWarps : 0)) * 32, smem, st>>>(L);
-  BS_CUDA(cudaGetLastError());
+  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
+                     smem, st, L));
   return 0;
 }
 
