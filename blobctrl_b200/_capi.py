@@ -16,7 +16,7 @@ F32, F64, BF16, F16 = 0, 1, 2, 3
 SELECT_ALL, SELECT_FG, SELECT_BG = 0, 1, 2
 COMPOSITE_AUTO, COMPOSITE_LANE_PIXEL, COMPOSITE_WARP_SCAN = 0, 1, 2
 ENGINE_AUTO, ENGINE_FMA, ENGINE_TENSOR = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -28,7 +28,17 @@ class BlobSplatLibraryError(RuntimeError):
 
 
 class BlobSplatError(RuntimeError):
-    """A C-ABI call returned a negative status."""
+    """A C-ABI call returned a negative status (base class of the two below)."""
+
+
+class BlobSplatUnsupported(BlobSplatError):
+    """Status -2: the shape / dtype is outside the envelope of the requested kernel.  Nothing was launched, the CUDA
+    context is untouched — the only status a caller may answer by choosing another engine."""
+
+
+class BlobSplatCudaError(BlobSplatError):
+    """Status -3: a CUDA call failed (launch error, trap in a kernel, sticky context error).  Never retried, never
+    answered with another engine: the context may be poisoned and the caller has to see it."""
 
 
 class Caps(ctypes.Structure):
@@ -44,6 +54,7 @@ SIGNATURES = {
     "blobsplat_last_error": [ctypes.c_char_p, ctypes.c_size_t],
     "blobsplat_scores": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
     "blobsplat_scores_ellipse": [_P, _P, ctypes.c_float, ctypes.c_float, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P],
+    "blobsplat_preview": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "blobsplat_composite": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_resize_bilinear": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_pyramid": [_P, ctypes.POINTER(_P), _I, _I, _I, _I, _I, _P],
@@ -51,6 +62,8 @@ SIGNATURES = {
     "blobsplat_feature_splat_levels": [_I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _P],
     "blobsplat_conditioning_fill": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_residual_inject": [_P, _P, _P, ctypes.c_float, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "blobsplat_conv_in_weights": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "blobsplat_conv_in_hoisted": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_render": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     "blobsplat_render_multiscale": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P],
 }
@@ -104,8 +117,8 @@ def check(status: int) -> None:
     if status == -1:
         raise ValueError(f"blobsplat: invalid argument: {msg}")
     if status == -2:
-        raise BlobSplatError(f"blobsplat: unsupported: {msg}")
-    raise BlobSplatError(f"blobsplat: CUDA failure: {msg}")
+        raise BlobSplatUnsupported(f"blobsplat: unsupported: {msg}")
+    raise BlobSplatCudaError(f"blobsplat: CUDA failure (status {status}): {msg}")
 
 
 def dtype_code(dt: torch.dtype) -> int:

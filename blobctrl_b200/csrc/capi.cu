@@ -40,6 +40,11 @@ int render_tc_dispatch(const float*, const float*, const float*, const float*, c
 int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, int, int, int, int, int, int, int,
                                cudaStream_t);
 int residual_inject_dispatch(void*, const void*, const float*, float, int, int, int, int, int, int, int, cudaStream_t);
+int preview_dispatch(const void*, const void*, const void*, const float*, int, const void*, int, int, int, int, int, void*, void*,
+                     cudaStream_t);
+int conv_in_weights_dispatch(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
+int conv_in_hoisted_dispatch(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int, int, int,
+                             int, int, int, cudaStream_t);
 int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtype, const char** why);
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
@@ -114,6 +119,19 @@ int blobsplat_scores_ellipse(const float* ellipses, const float* sizes, float im
   if (g.status) return g.status;
   return scores_ellipse_dispatch(ellipses, sizes, img_w, img_h, N, M, H, W, select, composed, composed_dtype, raw, raw_dtype,
                                  (cudaStream_t)stream);
+}
+
+int blobsplat_preview(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype, const void* colors,
+                      int colors_per_image, int N, int M, int H, int W, void* image, void* composed, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1, "bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+  BS_CHECK_ARG(M <= kMaxBlobs && N <= 65535 && (long long)H * W < (1ll << 31), "shape too large");
+  BS_CHECK_ARG(param_dtype == BLOBSPLAT_F32 || param_dtype == BLOBSPLAT_F64, "preview renders float32 or float64 (got %d)", param_dtype);
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(image && colors, "NULL image / colour pointer");
+  BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return preview_dispatch(xs, ys, covs, sizes, param_dtype, colors, colors_per_image, N, M, H, W, image, composed, (cudaStream_t)stream);
 }
 
 int blobsplat_composite(const void* scores_in, void* composed, int N, int K, int H, int W, int dtype, int device,
@@ -245,6 +263,35 @@ int blobsplat_residual_inject(void* hidden, const void* residual, const float* s
   DeviceGuard g(device);
   if (g.status) return g.status;
   return residual_inject_dispatch(hidden, residual, scale_per_sample, scale, B, C, H, Wh, Wr, cols, dtype, (cudaStream_t)stream);
+}
+
+int blobsplat_conv_in_weights(const void* weight, const void* features, float* weff, int B, int O, int Cin, int lc, int C, int K,
+                              int dtype, int device, void* stream) {
+  BS_CHECK_ARG(B >= 0 && O >= 1 && lc >= 0 && C >= 1 && K >= 1, "bad shape B=%d O=%d lc=%d C=%d K=%d", B, O, lc, C, K);
+  BS_CHECK_ARG(Cin == lc + 1 + C, "weight has %d input planes, expected lc + 1 + C = %d", Cin, lc + 1 + C);
+  BS_CHECK_ARG(valid_dtype(dtype) && dtype != BLOBSPLAT_F64, "float32 / bfloat16 / float16 only");
+  if (B == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(weight && features && weff, "NULL pointer");
+  BS_CHECK_ARG(B <= 65535, "batch too large");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return conv_in_weights_dispatch(weight, features, weff, B, O, Cin, lc, C, K, dtype, (cudaStream_t)stream);
+}
+
+int blobsplat_conv_in_hoisted(const void* latents, const void* cond, const void* weight, const void* bias, const float* weff,
+                              void* out, int B, int O, int Cin, int lc, int J, int h, int w, int halves, int dtype, int device,
+                              void* stream) {
+  BS_CHECK_ARG(B >= 0 && O >= 1 && lc >= 1 && J >= 1 && h >= 1 && w >= 1, "bad shape B=%d O=%d lc=%d J=%d h=%d w=%d", B, O, lc, J, h, w);
+  BS_CHECK_ARG(halves == 1 || halves == 2, "halves must be 1 or 2 (got %d)", halves);
+  BS_CHECK_ARG(Cin >= lc, "weight has %d input planes < lc = %d", Cin, lc);
+  BS_CHECK_ARG(valid_dtype(dtype) && dtype != BLOBSPLAT_F64, "float32 / bfloat16 / float16 only");
+  if (B == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(latents && cond && weight && weff && out, "NULL pointer");
+  BS_CHECK_ARG(B <= 65535 && (O + 31) / 32 <= 65535, "batch / channel count too large");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return conv_in_hoisted_dispatch(latents, cond, weight, bias, weff, out, B, O, Cin, lc, J, h, w, halves * w, dtype,
+                                  (cudaStream_t)stream);
 }
 
 int blobsplat_render(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,

@@ -184,3 +184,195 @@ int residual_inject_dispatch(void* hidden, const void* residual, const float* sc
 }
 
 }  // namespace blobsplat
+
+namespace blobsplat {
+
+// N1: loop-invariant hoist of BlobNet's conv_in.
+//
+// BlobNet's first layer is Conv2d(lc + 1 + C, O, 3, padding = 1) (blobctrl/models/blobnet.py:241-245, applied at :840) over
+// the canvas construct_blobnet_input builds every step (blobctrl/pipelines/pipeline_blobnet.py:724-739, :1043-1049):
+// lc = 4 latent planes, one score plane, C = 1024 feature planes, left half = reference-image latents, right half =
+// noisy latents, the conditioning planes identical in both halves.  The feature planes are rank-K
+// (feats[c] = sum_k s_k * f[k, c], :984) and convolution is linear, so
+//
+//   conv_in(canvas)[b, o] = bias[o] + sum_{c < lc} W[o, c] * lat[b, c]                       <- changes every step
+//                         + W[o, lc] * score[b]  +  sum_k W_eff[b, o, k] * s_k[b]             <- loop-invariant planes
+//   W_eff[b, o, k, tap] = sum_c W[o, lc + 1 + c, tap] * f[b, k, c]                            <- once per edit
+//
+// i.e. a (lc + 1 + K) -> O convolution with per-sample kernels for the conditioning planes instead of a 1029 -> 320 one
+// (~48.6 GFLOP per sample and step), and neither the 1024 feature planes nor the 1029-plane canvas are ever built.
+//
+// conv_in_weights_kernel: one block per (sample, output channel): the 9 * K dot products over C.
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256)
+conv_in_weights_kernel(const T* __restrict__ weight, const T* __restrict__ feats, float* __restrict__ weff, int O, int Cin,
+                       int lc, int C, int K, int Jp) {
+  // weff [B, O, Jp, 12]: plane 0 = the score plane's own kernel W[o, lc]; plane 1 + k = W_eff[b, o, k]; 9 taps padded to 12
+  const int o = blockIdx.x, b = blockIdx.y;
+  const T* w = weight + ((size_t)o * Cin + lc + 1) * 9;       // [C][9] contiguous
+  const T* f = feats + (size_t)b * K * C;
+  __shared__ float red[8][KMAX * 9];
+  for (int k0 = 0; k0 < K; k0 += KMAX) {
+    const int kn = min(KMAX, K - k0);
+    float acc[KMAX][9];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[k][t] = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float wv[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) wv[t] = (float)Cvt<T>::to(w[(size_t)c * 9 + t]);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < kn) {
+          const float fv = (float)Cvt<T>::to(f[(size_t)(k0 + k) * C + c]);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[k][t] = fmaf(wv[t], fv, acc[k][t]);
+        }
+      }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float v = acc[k][t];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][k * 9 + t] = v;
+      }
+    __syncthreads();
+    if ((int)threadIdx.x < kn * 9) {
+      float v = 0.f;
+      for (int wi = 0; wi < (int)(blockDim.x >> 5); ++wi) v += red[wi][threadIdx.x];
+      const int k = threadIdx.x / 9, t = threadIdx.x - k * 9;
+      weff[(((size_t)b * O + o) * Jp + 1 + k0 + k) * 12 + t] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 9) weff[(((size_t)b * O + o) * Jp) * 12 + threadIdx.x] = (float)Cvt<T>::to(weight[((size_t)o * Cin + lc) * 9 + threadIdx.x]);
+}
+
+// conv_in_hoisted_kernel: the per-step layer.  Block = 64 threads x 2 pixels (x and x + 64 of a 128-pixel row segment)
+// x kOcT output channels; the (lc + J) input planes' 3-row halo and the block's kernels live in shared memory, the kernels
+// padded to 12 floats so a thread fetches one (output channel, plane) kernel with three broadcast LDS.128 for its 18 FMAs.
+constexpr int kOcT = 32;
+template <typename T>
+__global__ void __launch_bounds__(64)
+conv_in_hoisted_kernel(const T* __restrict__ lat, const T* __restrict__ cond, const T* __restrict__ weight,
+                       const T* __restrict__ bias, const float* __restrict__ weff, T* __restrict__ out, int O, int Cin, int lc,
+                       int J, int h, int w, int Wt) {
+  extern __shared__ __align__(16) float sm[];
+  const int planes = lc + J;
+  float* wsm = sm;                                   // [kOcT][planes][12]
+  float* in = sm + (size_t)kOcT * planes * 12;       // [planes][3][130]
+  const int xt = blockIdx.x % ((Wt + 127) / 128), y = blockIdx.x / ((Wt + 127) / 128);
+  const int o0 = blockIdx.y * kOcT, b = blockIdx.z;
+  const int x0 = xt * 128;
+  for (int i = threadIdx.x; i < kOcT * planes * 12; i += 64) {
+    const int t = i % 12, pl = (i / 12) % planes, oc = i / (12 * planes);
+    float v = 0.f;
+    if (t < 9 && o0 + oc < O)
+      v = pl < lc ? (float)Cvt<T>::to(weight[((size_t)(o0 + oc) * Cin + pl) * 9 + t])
+                  : weff[(((size_t)b * O + o0 + oc) * J + (pl - lc)) * 12 + t];
+    wsm[i] = v;
+  }
+  for (int i = threadIdx.x; i < planes * 3 * 130; i += 64) {
+    const int xx = i % 130, r = (i / 130) % 3, pl = i / 390;
+    const int gx = x0 + xx - 1, gy = y + r - 1;
+    float v = 0.f;
+    if (gx >= 0 && gx < Wt && gy >= 0 && gy < h)
+      v = pl < lc ? (float)Cvt<T>::to(lat[(((size_t)b * lc + pl) * h + gy) * Wt + gx])
+                  : (float)Cvt<T>::to(cond[(((size_t)b * J + (pl - lc)) * h + gy) * w + (gx % w)]);   // same planes in every half
+    in[i] = v;
+  }
+  __syncthreads();
+  float acc0[kOcT], acc1[kOcT];
+#pragma unroll
+  for (int oc = 0; oc < kOcT; ++oc) {
+    const float bv = (bias && o0 + oc < O) ? (float)Cvt<T>::to(bias[o0 + oc]) : 0.f;
+    acc0[oc] = bv; acc1[oc] = bv;
+  }
+  const int tx = threadIdx.x;
+  for (int pl = 0; pl < planes; ++pl) {
+    float a[9], c[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        a[r * 3 + d] = in[(pl * 3 + r) * 130 + tx + d];
+        c[r * 3 + d] = in[(pl * 3 + r) * 130 + tx + 64 + d];
+      }
+#pragma unroll
+    for (int oc = 0; oc < kOcT; ++oc) {
+      const float4* wp = reinterpret_cast<const float4*>(wsm + ((size_t)oc * planes + pl) * 12);
+      const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+      const float wv[9] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x};
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        acc0[oc] = fmaf(wv[t], a[t], acc0[oc]);
+        acc1[oc] = fmaf(wv[t], c[t], acc1[oc]);
+      }
+    }
+  }
+  const int gx0 = x0 + tx, gx1 = x0 + tx + 64;
+#pragma unroll
+  for (int oc = 0; oc < kOcT; ++oc) {
+    if (o0 + oc >= O) break;
+    T* orow = out + (((size_t)b * O + o0 + oc) * h + y) * Wt;
+    if (gx0 < Wt) orow[gx0] = Cvt<T>::from(acc0[oc]);
+    if (gx1 < Wt) orow[gx1] = Cvt<T>::from(acc1[oc]);
+  }
+}
+
+template <typename T>
+static int launch_conv_in_weights(const void* weight, const void* feats, float* weff, int B, int O, int Cin, int lc, int C, int K,
+                                  cudaStream_t st) {
+  conv_in_weights_kernel<T, 4><<<dim3((unsigned)O, (unsigned)B), 256, 0, st>>>((const T*)weight, (const T*)feats, weff, O, Cin, lc,
+                                                                              C, K, 1 + K);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_in_weights_dispatch(const void* weight, const void* feats, float* weff, int B, int O, int Cin, int lc, int C, int K,
+                             int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case BLOBSPLAT_F32: return launch_conv_in_weights<float>(weight, feats, weff, B, O, Cin, lc, C, K, st);
+    case BLOBSPLAT_BF16: return launch_conv_in_weights<__nv_bfloat16>(weight, feats, weff, B, O, Cin, lc, C, K, st);
+    case BLOBSPLAT_F16: return launch_conv_in_weights<__half>(weight, feats, weff, B, O, Cin, lc, C, K, st);
+  }
+  BS_UNSUPPORTED("conv_in hoist supports float32/bfloat16/float16 (got %d)", dtype);
+}
+
+template <typename T>
+static int launch_conv_in_hoisted(const void* lat, const void* cond, const void* weight, const void* bias, const float* weff,
+                                  void* out, int B, int O, int Cin, int lc, int J, int h, int w, int Wt, cudaStream_t st) {
+  const int planes = lc + J;
+  const size_t smem = ((size_t)kOcT * planes * 12 + (size_t)planes * 3 * 130) * sizeof(float);
+  if (smem > 200 * 1024) BS_UNSUPPORTED("conv_in hoist: %d input planes do not fit in shared memory", planes);
+  static thread_local int configured_dev = -1;
+  int dev = 0;
+  BS_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    BS_CUDA(cudaFuncSetAttribute(conv_in_hoisted_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured_dev = dev;
+  }
+  dim3 grid((unsigned)(((Wt + 127) / 128) * h), (unsigned)((O + kOcT - 1) / kOcT), (unsigned)B);
+  conv_in_hoisted_kernel<T><<<grid, 64, smem, st>>>((const T*)lat, (const T*)cond, (const T*)weight, (const T*)bias, weff, (T*)out,
+                                                   O, Cin, lc, J, h, w, Wt);
+  BS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_in_hoisted_dispatch(const void* lat, const void* cond, const void* weight, const void* bias, const float* weff, void* out,
+                             int B, int O, int Cin, int lc, int J, int h, int w, int Wt, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case BLOBSPLAT_F32: return launch_conv_in_hoisted<float>(lat, cond, weight, bias, weff, out, B, O, Cin, lc, J, h, w, Wt, st);
+    case BLOBSPLAT_BF16: return launch_conv_in_hoisted<__nv_bfloat16>(lat, cond, weight, bias, weff, out, B, O, Cin, lc, J, h, w, Wt, st);
+    case BLOBSPLAT_F16: return launch_conv_in_hoisted<__half>(lat, cond, weight, bias, weff, out, B, O, Cin, lc, J, h, w, Wt, st);
+  }
+  BS_UNSUPPORTED("conv_in hoist supports float32/bfloat16/float16 (got %d)", dtype);
+}
+
+}  // namespace blobsplat

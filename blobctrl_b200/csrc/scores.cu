@@ -254,6 +254,91 @@ scores_warp_scan_f32(const float* __restrict__ xs, const float* __restrict__ ys,
   }
 }
 
+// ---- preview: stages 1+2 + the C = 3 colour splat in ONE launch ----------------------------------------
+// The UI preview (scripts/blobctrl_app.py:637-650 -> utils.py:198-223 with only_vis=True) needs only
+// feature_img[n, ch, y, x] = sum_k d_k * colour[k, ch] (utils.py:244-270 with an identity viz_score_fn): the
+// composed maps never have to exist.  One thread = V adjacent pixels, front-to-back walk with the
+// transmittance in a register (as above), the colour table in shared memory.  PT = float: whitened
+// coefficients (common.cuh); PT = double: the reference's fp64 arithmetic, as scores_lane_pixel_f64.
+template <typename PT, int V>
+__global__ void __launch_bounds__(kScoreThreads)
+preview_kernel(const PT* __restrict__ xs, const PT* __restrict__ ys, const PT* __restrict__ covs,
+               const float* __restrict__ sizes, const PT* __restrict__ colors, int colors_per_image, int M, int H, int W,
+               PT* __restrict__ image, PT* __restrict__ composed) {
+  constexpr bool kF64 = sizeof(PT) == 8;
+  using Coef = typename std::conditional<kF64, BlobCoefD, BlobCoef>::type;
+  __shared__ Coef coef[kBlobChunk];
+  __shared__ PT col[kBlobChunk + 1][3];
+  const int n = blockIdx.y;
+  const int P = H * W;
+  const int pix = (blockIdx.x * kScoreThreads + threadIdx.x) * V;
+  const bool active = pix < P;
+  const int y = active ? pix / W : 0;
+  const int x = active ? pix - y * W : 0;
+  const PT* cb = colors + (colors_per_image ? (size_t)n * (M + 1) * 3 : 0);
+  PT T[V], rgb[3][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { T[j] = (PT)1; rgb[0][j] = rgb[1][j] = rgb[2][j] = (PT)0; }
+  PT* cbase = composed ? composed + (size_t)n * (M + 1) * P + pix : nullptr;
+
+  for (int hi = M; hi > 0; hi -= kBlobChunk) {
+    const int lo = hi > kBlobChunk ? hi - kBlobChunk : 0;
+    const int cnt = hi - lo;
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt; i += kScoreThreads) {
+      const size_t b = (size_t)n * M + lo + i;
+      const PT* c = covs + 4 * b;
+      if constexpr (kF64) {
+        const double det = c[0] * c[3] - c[1] * c[2];
+        BlobCoefD o;
+        o.cx = xs[b] * (double)W; o.cy = ys[b] * (double)H;
+        o.A = (c[3] / det) / ((double)W * (double)W);
+        o.B2 = (-(c[1] + c[2]) / det) / ((double)W * (double)H);
+        o.C = (c[0] / det) / ((double)H * (double)H);
+        o.gated = sizes[b] < 0.5f;
+        coef[i] = o;
+      } else {
+        coef[i] = make_blob_coef((double)xs[b], (double)ys[b], (double)c[0], (double)c[1], (double)c[2], (double)c[3],
+                                 sizes[b], H, W);
+      }
+      for (int ch = 0; ch < 3; ++ch) col[i][ch] = cb[(size_t)(lo + i + 1) * 3 + ch];
+    }
+    __syncthreads();
+    if (!active) continue;
+    for (int i = cnt - 1; i >= 0; --i) {
+      const Coef c = coef[i];
+      PT d[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        PT s;
+        if constexpr (kF64) {
+          const double dx = (double)(x + j) - c.cx, dy = (double)y - c.cy;
+          const double q = dx * (c.A * dx + c.B2 * dy) + c.C * dy * dy;
+          s = c.gated ? (double)1e-6f : fmin(2.0 / (1.0 + exp(q)), 1.0);
+          d[j] = s * T[j];
+          T[j] = T[j] * (1.0 - s);
+        } else {
+          s = blob_opacity(c, (float)(x + j), (float)y);
+          d[j] = s * T[j];
+          T[j] = fmaf(-s, T[j], T[j]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) rgb[ch][j] += d[j] * col[i][ch];
+      }
+      if (cbase) VecStore<PT, V>::st(cbase + (size_t)(lo + i + 1) * P, d);
+    }
+  }
+  if (!active) return;
+  if (cbase) VecStore<PT, V>::st(cbase, T);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    PT v[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = rgb[ch][j] + T[j] * cb[ch];          // background: alpha 1 * transmittance
+    VecStore<PT, V>::st(image + ((size_t)n * 3 + ch) * P + pix, v);
+  }
+}
+
 // ---- composite only (viz_score_fn branch, utils.py:205-206) -------------------------------------------
 template <typename T, typename A>
 __global__ void __launch_bounds__(256)
@@ -371,6 +456,34 @@ int scores_ellipse_dispatch(const float* ell, const float* sizes, float img_w, f
     case BLOBSPLAT_F16: return launch_lane_pixel_f32<__half>(nullptr, nullptr, nullptr, sizes, N, M, H, W, select, ksel, composed, raw, st, ell, img_w, img_h);
   }
   BS_UNSUPPORTED("ellipse front end renders float32/bfloat16/float16 maps (got dtype %d)", odt);
+}
+
+int preview_dispatch(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype, const void* colors,
+                     int colors_per_image, int N, int M, int H, int W, void* image, void* composed, cudaStream_t st) {
+  const int P = H * W;
+  if (param_dtype == BLOBSPLAT_F64) {
+    const bool vec = (W % 2 == 0) && aligned_to(image, 16) && aligned_to(composed, 16);
+    dim3 grid((unsigned)((P / (vec ? 2 : 1) + kScoreThreads - 1) / kScoreThreads), (unsigned)N);
+    if (vec)
+      preview_kernel<double, 2><<<grid, kScoreThreads, 0, st>>>((const double*)xs, (const double*)ys, (const double*)covs, sizes,
+                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed);
+    else
+      preview_kernel<double, 1><<<grid, kScoreThreads, 0, st>>>((const double*)xs, (const double*)ys, (const double*)covs, sizes,
+                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed);
+  } else if (param_dtype == BLOBSPLAT_F32) {
+    const bool vec = (W % 4 == 0) && aligned_to(image, 16) && aligned_to(composed, 16);
+    dim3 grid((unsigned)((P / (vec ? 4 : 1) + kScoreThreads - 1) / kScoreThreads), (unsigned)N);
+    if (vec)
+      preview_kernel<float, 4><<<grid, kScoreThreads, 0, st>>>((const float*)xs, (const float*)ys, (const float*)covs, sizes,
+                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed);
+    else
+      preview_kernel<float, 1><<<grid, kScoreThreads, 0, st>>>((const float*)xs, (const float*)ys, (const float*)covs, sizes,
+                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed);
+  } else {
+    BS_UNSUPPORTED("preview renders float32 or float64 (got %d)", param_dtype);
+  }
+  BS_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int composite_dispatch(const void* in, void* out, int N, int K, int H, int W, int dtype, cudaStream_t st) {

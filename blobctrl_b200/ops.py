@@ -212,10 +212,10 @@ def feature_splat_levels(scores: Sequence[torch.Tensor], features: Sequence[torc
 def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width: int,
                  out_dtype: Optional[torch.dtype] = None, want_composed: bool = True):
     """Stages 1+2+3 in one launch (blobsplat_render, tcgen05).  Returns (composed | None, grid).
-    Raises BlobSplatError when the shape is outside the tensor-core kernel's envelope."""
+    Raises BlobSplatUnsupported when the shape is outside the tensor-core kernel's envelope."""
     xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
     if covs_c.dtype != torch.float32:
-        raise C.BlobSplatError("blobsplat: unsupported: fused render takes float32 blob parameters")
+        raise C.BlobSplatUnsupported("blobsplat: unsupported: fused render takes float32 blob parameters")
     if out_dtype is None:
         out_dtype = features.dtype
     f = features.to(device=covs_c.device, dtype=out_dtype).contiguous()     # utils.py:69
@@ -237,7 +237,7 @@ def render_multiscale(xs, ys, covs, sizes, size: int, level_features: Sequence[O
     Returns (composed maps per level, grids per level (None where no features)).  One C call for the whole pyramid."""
     xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
     if covs_c.dtype != torch.float32:
-        raise C.BlobSplatError("blobsplat: unsupported: fused render takes float32 blob parameters")
+        raise C.BlobSplatUnsupported("blobsplat: unsupported: fused render takes float32 blob parameters")
     dev = covs_c.device
     L = len(level_features)
     feats, comps, grids, cs = [], [], [], []
@@ -300,3 +300,64 @@ def render_scores_from_ellipses(ellipses: torch.Tensor, sizes: Optional[torch.Te
                                              _SELECT[select], C.ptr(composed), oc, C.ptr(raw), oc, C.dev_of(e),
                                              C.stream_of(e)))
     return composed, raw
+
+
+def render_preview(xs, ys, covs, sizes, colors: torch.Tensor, height: int, width: int, want_composed: bool = False):
+    """Stages 1+2 + the C = 3 colour splat in one launch (blobsplat_preview): image [N,3,H,W] = sum_k d_k * colors[k]
+    without materialising the score maps.  colors: [K, 3] or [N, K, 3] (K = M + 1 rows are read).  float32 or float64
+    (the dtype of ``covs``).  Returns (image, composed | None)."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    dt, dev = covs_c.dtype, covs_c.device
+    col = colors.to(device=dev, dtype=dt)
+    if col.ndim == 2:
+        col, per_image = col[: m + 1].contiguous(), 0
+    elif col.ndim == 3 and col.shape[0] == n:
+        col, per_image = col[:, : m + 1].contiguous(), 1
+    else:
+        raise RuntimeError(f"colors must be [K, 3] or [N, K, 3], got {tuple(colors.shape)}")
+    if col.shape[-2] < m + 1 or col.shape[-1] != 3:
+        raise RuntimeError(f"colors must hold {m + 1} RGB rows, got {tuple(colors.shape)}")
+    image = C.new_output((n, 3, height, width), dt, dev)
+    composed = C.new_output((n, m + 1, height, width), dt, dev) if want_composed else None
+    C.check(C.lib().blobsplat_preview(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.dtype_code(dt), C.ptr(col), per_image,
+                                      n, m, height, width, C.ptr(image), C.ptr(composed), C.dev_of(covs_c), C.stream_of(covs_c)))
+    return image, composed
+
+
+def conv_in_weights(weight: torch.Tensor, features: torch.Tensor, latent_channels: int = 4) -> torch.Tensor:
+    """blobsplat_conv_in_weights: per-sample effective 3x3 kernels of the conditioning planes of BlobNet's conv_in.
+    weight [O, lc+1+C, 3, 3], features [B, K, C] -> weff [B, O, 1+K, 12] float32 (9 taps padded to 12)."""
+    C.require_cuda(weight, "weight")
+    w = weight.contiguous()
+    f = features.to(device=w.device, dtype=w.dtype).contiguous()
+    o, cin = w.shape[:2]
+    b, k, c = f.shape
+    if w.shape[2:] != (3, 3) or cin != latent_channels + 1 + c:
+        raise RuntimeError(f"conv_in weight {tuple(w.shape)} does not match {latent_channels} latent + 1 score + {c} feature planes")
+    weff = torch.zeros((b, o, 1 + k, 12), dtype=torch.float32, device=w.device)
+    C.check(C.lib().blobsplat_conv_in_weights(C.ptr(w), C.ptr(f), C.ptr(weff), b, o, cin, latent_channels, c, k,
+                                              C.dtype_code(w.dtype), C.dev_of(w), C.stream_of(w)))
+    return weff
+
+
+def conv_in_hoisted(latents: torch.Tensor, cond: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                    weff: torch.Tensor, halves: int = 2, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """blobsplat_conv_in_hoisted: latents [B, lc, h, halves*w], cond [B, J, h, w], weight [O, Cin, 3, 3], weff [B, O, J, 12]
+    -> [B, O, h, halves*w] == conv_in(construct_blobnet_input(...)) up to summation order."""
+    C.require_cuda(latents, "latents")
+    dt = latents.dtype
+    b, lc, h, wt = latents.shape
+    j, w = cond.shape[1], cond.shape[3]
+    o, cin = weight.shape[:2]
+    if wt != halves * w or cond.shape[0] != b or cond.shape[2] != h or tuple(weff.shape) != (b, o, j, 12):
+        raise RuntimeError("conv_in_hoisted: shape mismatch between latents, cond and weff")
+    for t in (latents, cond, weight, weff) + ((bias,) if bias is not None else ()):
+        if not (t.is_cuda and t.is_contiguous()):
+            raise RuntimeError("conv_in_hoisted needs contiguous CUDA tensors")
+    if cond.dtype != dt or weight.dtype != dt or (bias is not None and bias.dtype != dt) or weff.dtype != torch.float32:
+        raise RuntimeError("conv_in_hoisted: latents, cond, weight and bias must share a dtype; weff is float32")
+    if out is None:
+        out = C.new_output((b, o, h, wt), dt, latents.device)
+    C.check(C.lib().blobsplat_conv_in_hoisted(C.ptr(latents), C.ptr(cond), C.ptr(weight), C.ptr(bias), C.ptr(weff), C.ptr(out), b, o,
+                                              cin, lc, j, h, w, halves, C.dtype_code(dt), C.dev_of(latents), C.stream_of(latents)))
+    return out

@@ -113,21 +113,38 @@ class BlobNetInputBuffers:
 def inject_residual(hidden: torch.Tensor, residual: torch.Tensor, conditioning_scale=1.0) -> torch.Tensor:
     """N4: ``hidden[..., -h:] += conditioning_scale * residual[..., -h:]`` in place, one pass (h = hidden.shape[-2]; on a
     square map the whole width).  Fuses models/blobnet.py:936-938, pipeline_blobnet.py:1085-1087 and
-    unet_2d_condition.py:1215-1219.  ``conditioning_scale``: float or a per-sample tensor [B]."""
+    unet_2d_condition.py:1215-1219.  ``conditioning_scale``: float or a per-sample tensor [B].
+
+    ``residual`` is either the full map [B, C, H, Wr] or the right-hand crop the reference pipeline passes
+    (``residual[..., -h:]``, pipeline_blobnet.py:1085-1087 — a strided view): the crop is consumed in place through its
+    row stride, never copied."""
     from .. import _capi as C
     C.require_cuda(hidden, "hidden")
-    if not (hidden.is_contiguous() and residual.is_contiguous()) or hidden.dtype != residual.dtype:
-        raise RuntimeError("inject_residual needs contiguous tensors of one dtype")
+    if not hidden.is_contiguous() or hidden.dtype != residual.dtype:
+        raise RuntimeError("inject_residual needs a contiguous hidden state and one dtype")
     b, c, h, wh = hidden.shape
-    wr = residual.shape[-1]
     cols = min(h, wh) if wh != h else wh
+    rptr, wr = residual.data_ptr(), residual.shape[-1]
+    if not residual.is_contiguous():
+        # the right-most `cols` columns of rows that are `wr_full` apart: hand the kernel the row start and the row pitch
+        sb, sc, sh, sw = residual.stride()
+        wr_full = sh
+        if (residual.shape[-1] != cols or sw != 1 or sc != h * wr_full or (b > 1 and sb != c * h * wr_full)
+                or residual.storage_offset() < wr_full - cols):
+            residual = residual.contiguous()
+            rptr, wr = residual.data_ptr(), residual.shape[-1]
+        else:
+            rptr, wr = residual.data_ptr() - (wr_full - cols) * residual.element_size(), wr_full
+    if tuple(residual.shape[:3]) != (b, c, h) or wr < cols:
+        raise RuntimeError(f"residual {tuple(residual.shape)} does not match hidden {tuple(hidden.shape)}")
     sb = None
     sc = 1.0
     if torch.is_tensor(conditioning_scale):
         sb = conditioning_scale.to(device=hidden.device, dtype=hidden.dtype).float().reshape(b).contiguous()
     else:
         sc = float(conditioning_scale)
-    C.check(C.lib().blobsplat_residual_inject(C.ptr(hidden), C.ptr(residual), C.ptr(sb), sc, b, c, h, wh, wr, cols,
+    import ctypes
+    C.check(C.lib().blobsplat_residual_inject(C.ptr(hidden), ctypes.c_void_p(rptr), C.ptr(sb), sc, b, c, h, wh, wr, cols,
                                               C.dtype_code(hidden.dtype), C.dev_of(hidden), C.stream_of(hidden)))
     return hidden
 

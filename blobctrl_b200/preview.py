@@ -13,6 +13,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from . import _capi as C
 from . import ops
 from .utils.utils import BLOB_VIS_COLORS
 
@@ -31,16 +32,22 @@ class GraphedBlobRenderer:
         self.params = torch.zeros(7 * nm, **f32)
         self.xs = self.params[:nm].view(n, m); self.ys = self.params[nm:2 * nm].view(n, m)
         self.covs = self.params[2 * nm:6 * nm].view(n, m, 2, 2); self.sizes = self.params[6 * nm:].view(n, m)
-        self.host = torch.zeros(7 * nm, dtype=torch.float32).pin_memory()
-        self._h = self.host.numpy()
-        self._h[2 * nm:6 * nm] = [1, 0, 0, 1] * nm; self._h[6 * nm:] = 1
-        self.params.copy_(self.host)
+        # pinned staging is double-buffered: block i is rewritten only after the H2D copy that last read it has run
+        # (an event per block), so back-to-back calls without a sync never render call i with call i+1's parameters
+        self._hosts = [torch.zeros(7 * nm, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._hs = [h.numpy() for h in self._hosts]
+        self._copied = [torch.cuda.Event(), torch.cuda.Event()]
+        self._turn = 0
+        for h in self._hs:
+            h[2 * nm:6 * nm] = [1, 0, 0, 1] * nm; h[6 * nm:] = 1
+        self.params.copy_(self._hosts[0])
         self.feats = None
+        self.colors = None
         if viz_colors is not None:
-            self.feats = viz_colors[: m + 1].to(**f32)[None].repeat(n, 1, 1).contiguous()     # utils.py:251-253
+            self.colors = viz_colors[: m + 1].to(**f32).contiguous()                          # utils.py:251-253
         elif channels:
             self.feats = torch.zeros((n, m + 1, channels), **f32)
-        self.takes_features = viz_colors is None and channels is not None
+        self.takes_features = viz_colors is None and bool(channels)
         self.stream = torch.cuda.Stream(device=dev)
         self._run()                                      # warm-up outside capture (loads the kernels)
         torch.cuda.current_stream(dev).wait_stream(self.stream)
@@ -52,11 +59,15 @@ class GraphedBlobRenderer:
         with torch.cuda.stream(self.stream):
             c = self.feats.shape[-1] if self.feats is not None else 0
             self.grid = None
+            if self.colors is not None:      # the UI preview: stages 1+2 + colour splat in one launch (blobsplat_preview)
+                self.grid, self.scores = ops.render_preview(self.xs, self.ys, self.covs, self.sizes, self.colors, self.h, self.w,
+                                                            want_composed=True)
+                return
             if self.feats is not None and c >= 64:
                 try:
                     self.scores, self.grid = ops.render_fused(self.xs, self.ys, self.covs, self.sizes, self.feats, self.h, self.w)
                     return
-                except Exception:
+                except C.BlobSplatUnsupported:   # outside the tensor-core envelope only; CUDA failures propagate
                     pass
             self.scores, _ = ops.render_scores(self.xs, self.ys, self.covs, self.sizes, self.h, self.w)
             if self.feats is not None:
@@ -66,18 +77,23 @@ class GraphedBlobRenderer:
     def __call__(self, xs, ys, covs, sizes=None, features=None):
         """Parameters: host arrays / tensors of any float dtype (the reference's callers build them with numpy on the
         host, blobctrl_inference.py:101-109); device tensors are accepted but cost a sync.  Returns (composed [N,M+1,H,W], grid | None) —
-        views of the renderer's static output buffers (valid until the next call)."""
+        views of the renderer's static output buffers: the next call overwrites them in stream order, so consume (or clone)
+        them on the current stream before calling again."""
         import numpy as np
         nm = self.n * self.m
         to_np = lambda t: t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t)
-        self._h[:nm] = to_np(xs).reshape(-1); self._h[nm:2 * nm] = to_np(ys).reshape(-1)
-        self._h[2 * nm:6 * nm] = to_np(covs).reshape(-1)
-        if sizes is not None:
-            self._h[6 * nm:] = to_np(sizes).reshape(-1)
+        i = self._turn
+        self._turn ^= 1
+        self._copied[i].synchronize()               # the copy that last read this pinned block has completed
+        h = self._hs[i]
+        h[:nm] = to_np(xs).reshape(-1); h[nm:2 * nm] = to_np(ys).reshape(-1)
+        h[2 * nm:6 * nm] = to_np(covs).reshape(-1)
+        h[6 * nm:] = 1 if sizes is None else to_np(sizes).reshape(-1)
         cur = torch.cuda.current_stream(self.params.device)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
-            self.params.copy_(self.host, non_blocking=True)
+            self.params.copy_(self._hosts[i], non_blocking=True)
+            self._copied[i].record(self.stream)
             if features is not None and self.takes_features:
                 self.feats.copy_(features, non_blocking=True)
             self.graph.replay()

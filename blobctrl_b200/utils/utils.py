@@ -120,6 +120,14 @@ def _render_hw(covs: Tensor, score_size, viz_size) -> Tuple[int, int]:
     return int(h), int(w)
 
 
+def _viz_same_size(viz_size, h: int, w: int) -> bool:
+    """visualize_features resizes the score maps to ``viz_size`` (utils.py:70-73); the one-launch preview applies when
+    that resize is the identity, i.e. the maps were rendered at viz_size."""
+    if isinstance(viz_size, int):
+        return viz_size == h == w
+    return viz_size is not None and (int(viz_size[0]), int(viz_size[1])) == (h, w)
+
+
 def splat_features(
         xs: Tensor,
         ys: Tensor,
@@ -148,8 +156,22 @@ def splat_features(
         else dict with scores_pyramid {size: [N,K,S,S]}, feature_grid [N,C,S,S], feature_img, entropy_img
         (+ xs, ys, covs, raw_scores [N,H,W,K], sizes, composed_scores [N,H,W,K], features when ret_layout).
     Extra keyword-only extensions (absent from the reference): ``out_dtype``, ``composite_mode``
-    ('auto' | 'lane_pixel' | 'warp_scan'), ``engine`` ('auto' | 'fma' | 'tensor').
+    ('auto' | 'lane_pixel' | 'warp_scan'), ``engine`` ('auto' | 'fma' | 'tensor'), ``cuda_graph`` (bool, default False:
+    replay a captured CUDA graph of this exact call — the latency path for N = 1; the returned tensors are then the
+    graph's static buffers, see blobctrl_b200/graphs.py).
     """
+    if kwargs.get("cuda_graph"):
+        # opt-in: replay a captured graph of this exact call (blobctrl_b200/graphs.py); outputs are static buffers
+        from .. import graphs
+        kw = {k: v for k, v in kwargs.items() if k != "cuda_graph"}
+        tensors = (xs, ys, covs, sizes, features, kw.get("viz_colors"))
+        if graphs.capturable(*tensors) and (viz_score_fn is None or viz_score_fn is _IDENTITY_VIZ_SCORE_FN):
+            key = ("splat_features", graphs.tensor_key(tensors), graphs.tensor_key((score_size, viz_size)), interp_size, is_viz,
+                   ret_layout, viz_score_fn is None, return_d_score, only_vis, only_splatting_fg, only_splatting_bg,
+                   tuple(sorted((k, v) for k, v in kw.items() if not torch.is_tensor(v))))
+            return graphs.call(key, lambda: splat_features(xs, ys, covs, sizes, score_size, interp_size, features, viz_size,
+                                                           is_viz, ret_layout, viz_score_fn, return_d_score, only_vis,
+                                                           only_splatting_fg, only_splatting_bg, **kw), keepalive=tensors)
     out_dtype = kwargs.get("out_dtype")
     composite_mode = kwargs.get("composite_mode", "auto")
     engine = kwargs.get("engine", "auto")
@@ -164,6 +186,14 @@ def splat_features(
         return d
 
     wants_grid = not only_vis
+    viz_colors = kwargs.get("viz_colors", None)
+    if (only_vis and is_viz and select == "all" and torch.is_tensor(viz_colors) and viz_colors.ndim in (2, 3)
+            and (viz_score_fn is None or viz_score_fn is _IDENTITY_VIZ_SCORE_FN) and out_dtype is None
+            and covs.dtype in (torch.float32, torch.float64) and _viz_same_size(viz_size, h, w)
+            and viz_colors.shape[-2] >= m + 1 and (viz_colors.ndim == 2 or viz_colors.shape[0] == covs.shape[0])):
+        # the UI preview (blobctrl_app.py:637-650): stages 1+2 and the colour splat in ONE launch, no score maps in HBM
+        img, _ = ops.render_preview(xs, ys, covs, sizes, viz_colors, h, w)
+        return {"feature_img": img}
     if wants_grid and interp_size is None:                              # utils.py:291 — `W > None`
         raise TypeError("'>' not supported between instances of 'int' and 'NoneType' (interp_size is required "
                         "unless return_d_score or only_vis)")
@@ -177,7 +207,7 @@ def splat_features(
             and covs.dtype != torch.float64):
         try:
             d, grid = ops.render_fused(xs, ys, covs, sizes, features, h, w, out_dtype=out_dtype or covs.dtype)
-        except C.BlobSplatError:
+        except C.BlobSplatUnsupported:
             if engine == "tensor":
                 raise
             d = grid = None                                             # outside the tensor kernel's envelope
@@ -237,7 +267,7 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
                                               [level_features.get(score_size >> l) for l in range(n_lv)], dt)
             return {"scores_pyramid": {score_size >> l: comps[l] for l in range(n_lv)},
                     "feature_grids": {score_size >> l: gl[l] for l in range(n_lv) if gl[l] is not None}}
-        except C.BlobSplatError:
+        except C.BlobSplatUnsupported:
             pass                                     # outside the fused render's envelope: the general path below
     grids = {}
     d = None
@@ -247,7 +277,7 @@ def splat_features_multiscale(xs: Tensor, ys: Tensor, covs: Tensor, sizes: Tenso
         try:
             d, grids[score_size] = ops.render_fused(xs, ys, covs, sizes, top, score_size, score_size,
                                                     out_dtype=out_dtype or covs.dtype)
-        except C.BlobSplatError:
+        except C.BlobSplatUnsupported:
             if engine == "tensor":
                 raise
             d = None
@@ -357,3 +387,51 @@ def get_blob_vis_img_from_blob_dict(blob, viz_size=64, score_size=64):
     return splat_features(**blob, interp_size=64, viz_size=viz_size, is_viz=True, ret_layout=True,
                           score_size=score_size, viz_score_fn=viz_score_fn, viz_colors=BLOB_VIS_COLORS,
                           only_vis=True)["feature_img"]
+
+
+# --------------------------------------------------------------------------------------------------
+# overlay helpers (host side, OpenCV) — same names and behaviour as utils.py:393-456; imported by the scripts
+# (scripts/blobctrl_app.py:26)
+# --------------------------------------------------------------------------------------------------
+def vis_scores(blob_d_score, viz_size):
+    """utils.py:393-402.  Like the reference it loads the colour table from ``BED_CONF_COLORS.pt`` in the working
+    directory (the reference ships no such file, so its own call raises FileNotFoundError too)."""
+    n_gaussians = blob_d_score.shape[1] - 1
+    scores_viz = blob_d_score.permute(0, 2, 3, 1)
+    viz_colors = torch.load("BED_CONF_COLORS.pt")
+    return visualize_features(viz_size=viz_size, n_gaussians=n_gaussians, scores=scores_viz, viz_colors=viz_colors)["feature_img"]
+
+
+def vis_gt_ellipse_from_norm_gs(img, gt_mus, gt_covs, color=None):
+    """utils.py:405-430 — img: [h, w, c] uint8; gt_mus: [n, 2], gt_covs: [n, 2, 2] normalised gaussians.  Returns a copy."""
+    import cv2
+    result = img.copy()
+    height, width, _ = img.shape
+    max_length = np.sqrt(width ** 2 + height ** 2)
+    for mu, cov in zip(gt_mus, gt_covs):
+        mean = tuple(v.numpy() for v in mu.cpu().unbind(-1))
+        xc, yc, a, b, angle = gaussian_to_ellipse(mean, cov.cpu().numpy())
+        ellipse = (xc * width, yc * height), (a * max_length * 2, b * max_length * 2), angle
+        if color is None:
+            color = [255, 0, 0]
+        cv2.ellipse(result, ellipse, color, 3)
+    return result
+
+
+def vis_gt_ellipse_from_norm_ellipse(img, norm_ellipse, color=None):
+    """utils.py:433-444 — draws in place on ``img`` and returns it."""
+    import cv2
+    height, width, _ = img.shape
+    max_length = np.sqrt(width ** 2 + height ** 2)
+    (xc, yc), (d1, d2), theta = norm_ellipse
+    ellipse = (xc * width, yc * height), (d1 * max_length, d2 * max_length), theta
+    cv2.ellipse(img, ellipse, [255, 0, 0] if color is None else color, 3)
+    return img
+
+
+def vis_gt_ellipse_from_ellipse(img, ellipse, color=None):
+    """utils.py:447-456 — draws the OpenCV ellipse ((xc, yc), (d1, d2), angle) in place on ``img`` and returns it."""
+    import cv2
+    (xc, yc), (d1, d2), theta = ellipse
+    cv2.ellipse(img, ((xc, yc), (d1, d2), theta), [255, 0, 0] if color is None else color, 3)
+    return img

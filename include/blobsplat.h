@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BLOBSPLAT_ABI_VERSION 1
+#define BLOBSPLAT_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define BLOBSPLAT_API __attribute__((visibility("default")))
@@ -123,6 +123,18 @@ BLOBSPLAT_API int blobsplat_scores_ellipse(const float* ellipses, const float* s
                              int device, void* stream);
 
 /*
+ * (1c) preview — stages 1+2 and the C = 3 colour splat in ONE launch, the score maps never materialised.  Replaces
+ *      splat_features(..., is_viz=True, only_vis=True, viz_score_fn=identity) — utils.py:198-223 -> visualize_features
+ *      (utils.py:244-270) -> splat_features_from_scores (utils.py:57-77) — i.e. the UI preview of
+ *      scripts/blobctrl_app.py:637-650:   image[n, ch, y, x] = sum_k d_k[n, y, x] * colors[k, ch].
+ *   param_dtype F32 or F64 = dtype of xs / ys / covs / colors / image / composed (the app renders in float64).
+ *   colors [K, 3] (colors_per_image = 0) or [N, K, 3] (1); image [N, 3, H, W]; composed [N, K, H, W] or NULL.
+ */
+BLOBSPLAT_API int blobsplat_preview(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype,
+                      const void* colors, int colors_per_image, int N, int M, int H, int W,
+                      void* image, void* composed, int device, void* stream);
+
+/*
  * (1b) composite only.  Replaces utils.py:179-181 / :205-206 applied to caller-modified raw scores
  *      (the `viz_score_fn` branch).  scores_in / composed: planar [N, K, H, W], same dtype.
  */
@@ -201,6 +213,29 @@ BLOBSPLAT_API int blobsplat_conditioning_fill(const void* scores, const void* fe
  */
 BLOBSPLAT_API int blobsplat_residual_inject(void* hidden, const void* residual, const float* scale_per_sample, float scale,
                               int B, int C, int H, int Wh, int Wr, int cols, int dtype, int device, void* stream);
+
+/*
+ * (3d) hoisted BlobNet conv_in.  BlobNet's first layer, Conv2d(lc + 1 + C, O, 3, padding=1)
+ *      (models/blobnet.py:241-245, applied at :840) over the canvas of construct_blobnet_input
+ *      (pipelines/pipeline_blobnet.py:724-739, rebuilt at :1043-1049 every step), split by linearity into the part that
+ *      changes per step (the lc latent planes) and the loop-invariant conditioning planes, whose C rank-K feature planes
+ *      (:984) collapse into per-sample 3x3 kernels.
+ *   blobsplat_conv_in_weights — once per edit:   weff [B, O, 1 + K, 12] float32 (9 taps padded to 12),
+ *        weff[b, o, 0]     = weight[o, lc]                                   (the score plane's own kernel)
+ *        weff[b, o, 1 + k] = sum_c weight[o, lc + 1 + c] * features[b, k, c]
+ *      weight [O, Cin = lc + 1 + C, 3, 3], features [B, K, C], same dtype (F32/BF16/F16).
+ *   blobsplat_conv_in_hoisted — every step:
+ *        out[b, o] = bias[o] + sum_{c < lc} weight[o, c] (*) latents[b, c] + sum_{j < J} weff[b, o, j] (*) cond2[b, j]
+ *      latents [B, lc, h, halves*w] (left = reference-image latents, right = noisy latents), cond [B, J = 1 + K, h, w]
+ *      (plane 0 = the canvas's score plane, planes 1.. = the K blob score planes; cond2 = cond repeated in every width
+ *      half, as the canvas holds it), out [B, O, h, halves*w].  fp32 accumulation, one rounding to the output dtype.
+ *      Equals conv_in(construct_blobnet_input(...)) up to summation order.
+ */
+BLOBSPLAT_API int blobsplat_conv_in_weights(const void* weight, const void* features, float* weff, int B, int O, int Cin,
+                              int lc, int C, int K, int dtype, int device, void* stream);
+BLOBSPLAT_API int blobsplat_conv_in_hoisted(const void* latents, const void* cond, const void* weight, const void* bias,
+                              const float* weff, void* out, int B, int O, int Cin, int lc, int J, int h, int w,
+                              int halves, int dtype, int device, void* stream);
 
 /*
  * (4) fused render — stages 1+2+3 in ONE launch: blob parameters + features -> composed score maps

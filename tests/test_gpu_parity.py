@@ -2,9 +2,12 @@
 (a) the golden fixtures recorded from the real reference and (b) the float64 numpy oracle on seeded
 inputs, plus size-independent properties at BASELINE.json's full sizes.
 
-Tolerances (BASELINE.json north_star; SURVEY.md §7.2 for the scale-relative definition):
-  fp32 maps : |got - ref| <= 1e-5 * max|ref| (+1e-5 elementwise-relative)   [scores live in [0,1]]
+Tolerances (BASELINE.json north_star; SURVEY.md §7.2 for the scale-relative definition) — never widened per test:
+  fp32 maps : |got - ref| <= 1e-5 * max|ref|   [scores live in [0,1]]; thin blobs are compared with the float64
+              reference on the same (float32-rounded) inputs, because the reference's own float32 run is 6.7e-6 abs
+              away from its float64 self there
   bf16 maps : |got - ref| <= 1e-2 * max|ref|
+  fp16 maps : 2e-3 (north_star names no f16 bar; 4 half-ulps of f16)
   fp64 maps : 1e-9 relative
   ordering / indexing (argmax_k, channel order, fg/bg selection): exact.
 """
@@ -59,9 +62,13 @@ def test_golden_cases(case):
             G.check_close(got, want, 1e-9 if f64 else 3e-5, 0, f"{case['name']}:{key}")
             continue
         assert got.dtype == want.dtype, (key, got.dtype, want.dtype)
-        # thin blobs in fp32: the reference's own LU solve is 6.7e-6 abs / 5e-3 rel from its fp64 self
-        rel = 1e-9 if f64 else (2e-5 if case["name"].startswith("thin") else 1e-5)
-        close_scaled(got, want, rel, f"{case['name']}:{key}")
+        if case["name"] == "thin_f32":
+            # thin blobs in fp32: the reference's own LU solve is 6.7e-6 abs / 5e-3 rel from its fp64 self, so the yardstick
+            # is the float64 reference arithmetic on the same float32 inputs (oracle pinned to the reference at 1e-13)
+            ins = G.case_inputs(case)
+            want = blob_oracle.splat_features(**{k: ins[k] for k in ("xs", "ys", "covs", "sizes")}, score_size=32,
+                                              return_d_score=True, dtype=np.float64)
+        close_scaled(got, want, 1e-9 if f64 else 1e-5, f"{case['name']}:{key}")
 
 
 def test_forty_demo_ellipses_fp64_script_recipe():
@@ -355,7 +362,7 @@ def test_tensor_engine_rejects_outside_envelope():
         U.splat_features_from_scores(big, torch.randn(1, 130, 64, device=DEV), 8, channels_last=False, engine="tensor")
     forced = U.splat_features_from_scores(sc, ft, 8, channels_last=False, engine="tensor")   # any C: ragged channel tile
     out = U.splat_features_from_scores(sc, ft, 8, channels_last=False)  # auto -> FMA (tiny K, C)
-    assert (forced - out).abs().max().item() <= 2e-5 * out.abs().max().item()
+    assert (forced - out).abs().max().item() <= 1e-5 * out.abs().max().item()
     want = torch.einsum("nkhw,nkc->nchw", sc, ft)
     assert (out - want).abs().max().item() <= 1e-5 * want.abs().max().item()
 
@@ -421,6 +428,7 @@ def test_ellipse_front_end_multi_blob_and_rect():
     n, m, img_h, img_w, h, w = 3, 6, 384, 640, 40, 72
     ell = np.stack([rng.uniform(0, img_w, (n, m)), rng.uniform(0, img_h, (n, m)), rng.uniform(20, 300, (n, m)),
                     rng.uniform(20, 300, (n, m)), rng.uniform(0, 180, (n, m))], -1)
+    ell = ell.astype(np.float32).astype(np.float64)      # the entry point takes float32 ellipses: same inputs on both sides
     sizes = (rng.random((n, m)) > 0.2).astype(np.float32)
     xs = np.zeros((n, m)); ys = np.zeros((n, m)); covs = np.zeros((n, m, 2, 2))
     for i in range(n):
@@ -435,7 +443,7 @@ def test_ellipse_front_end_multi_blob_and_rect():
     got = U.splat_ellipses(torch.from_numpy(ell).float().to(DEV), torch.from_numpy(sizes).to(DEV), image_size=(img_h, img_w),
                            score_size=(h, w))
     assert got.shape == (n, m + 1, h, w)
-    close_scaled(_np(got), want, 2e-5, "multi-blob ellipses")     # fp32 ellipse inputs: centre rounding ~3e-5 px
+    close_scaled(_np(got), want, 1e-5, "multi-blob ellipses")
     fg = U.splat_ellipses(torch.from_numpy(ell).float().to(DEV), torch.from_numpy(sizes).to(DEV), image_size=(img_h, img_w),
                           score_size=(h, w), only_splatting_fg=True)
     assert torch.equal(fg, got[:, 1:])
@@ -516,12 +524,12 @@ def test_randomised_shapes_vs_oracle():
         want_d = np.moveaxis(dref, -1, 1)
         b = _blob(syn)
         d, r = ops.render_scores(b["xs"], b["ys"], b["covs"], b["sizes"], h, w, want_raw=True)
-        close_scaled(_np(d), want_d, 2e-5 if it % 5 == 0 else 1e-5, f"case {it} composed {n}x{m}x{h}x{w}")
-        close_scaled(_np(r)[:, 1:], np.moveaxis(raw, -1, 1), 2e-5 if it % 5 == 0 else 1e-5, f"case {it} raw")
+        close_scaled(_np(d), want_d, 1e-5, f"case {it} composed {n}x{m}x{h}x{w}")
+        close_scaled(_np(r)[:, 1:], np.moveaxis(raw, -1, 1), 1e-5, f"case {it} raw")
         want_g = blob_oracle.splat_features_from_scores(want_d, syn["features"].astype(np.float64), None, channels_last=False)
         for eng in ("fma", "auto"):
             g = ops.feature_splat(d, _cuda(syn["features"]), engine=eng)
-            close_scaled(_np(g), want_g, 2e-5, f"case {it} grid C={c} {eng}")
+            close_scaled(_np(g), want_g, 1e-5, f"case {it} grid C={c} {eng}")
 
 
 def test_input_forms_noncontiguous_half_params_and_large_image():
@@ -612,7 +620,7 @@ def test_fused_render_epilogue_paths(h, w, c, dtype, rel):
     want_g = blob_oracle.splat_features_from_scores(want_d, _np(feats).astype(np.float64), None, channels_last=False)
     comp, grid = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w)
     close_scaled(_np(comp), want_d, rel, f"composed {h}x{w}")
-    close_scaled(_np(grid), want_g, 2 * rel, f"grid {h}x{w} C={c}")
+    close_scaled(_np(grid), want_g, rel, f"grid {h}x{w} C={c}")
     # same call into a buffer offset by one element: grid base not 8/16-byte aligned
     store = torch.zeros(n * c * h * w + 1, dtype=dtype, device=DEV)
     grid2 = store[1:].view(n, c, h, w)
@@ -690,12 +698,12 @@ def test_fused_render_schedules_and_staging_ring(n, m, h, w, c, dtype, rel):
     close_scaled(_np(comp), want_d, rel, f"composed N={n} M={m}")
     if m == 0:
         return
-    close_scaled(_np(grid), want_g, 2 * rel, f"grid N={n} M={m} C={c}")
+    close_scaled(_np(grid), want_g, rel, f"grid N={n} M={m} C={c}")
     # the stand-alone stage 3 on the same weights takes the other A source through the same schedules
     g2 = ops.feature_splat(comp, feats, engine="tensor")
     want_g2 = blob_oracle.splat_features_from_scores(_np(comp).astype(np.float64), _np(feats).astype(np.float64), None,
                                                      channels_last=False)
-    close_scaled(_np(g2), want_g2, 2 * rel, f"stage 3 from maps N={n} M={m} C={c}")
+    close_scaled(_np(g2), want_g2, rel, f"stage 3 from maps N={n} M={m} C={c}")
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -716,3 +724,224 @@ def test_render_multiscale_one_call_equals_the_call_sequence(dtype):
         assert torch.equal(comps[l], pyr[s >> l])
         if feats[l] is not None:
             assert torch.equal(grids[l], ops.feature_splat(pyr[s >> l], feats[l]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: preview kernel, graph paths, error propagation, pipeline-method fixtures, N1 kernels, the cfg4 loop
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,rel", [(torch.float32, 1e-5), (torch.float64, 1e-9)])
+def test_preview_one_launch_vs_oracle_and_the_three_launch_path(dtype, rel):
+    """blobsplat_preview (stages 1+2 + colour splat in one launch) == utils.py:198-223 + :244-270 on the oracle, and the
+    same image as the scores -> feature-splat path it replaces; multi-blob, per-image colours, H != W, gated blobs."""
+    from blobctrl_b200 import ops
+    U = _impl()
+    for (n, m, h, w, seed) in [(1, 1, 64, 64, 1), (3, 7, 20, 36, 2), (2, 28, 17, 9, 3), (2, 150, 8, 8, 4)]:
+        syn = blob_oracle.synthetic_blobs(n, m, seed=seed)
+        b = _blob(syn, dtype)
+        rng = np.random.default_rng(seed)
+        colors = rng.random((n, m + 1, 3)) if m > 28 or seed == 2 else blob_oracle.BLOB_VIS_COLORS.astype(np.float64)
+        raw = blob_oracle.raw_scores(_np(b["xs"]), _np(b["ys"]), _np(b["covs"]), syn["sizes"], h, w, np.float64)
+        _, d = blob_oracle.composite(raw)                                  # [N,H,W,K]
+        col = colors if colors.ndim == 3 else np.broadcast_to(colors[: m + 1], (n, m + 1, 3))
+        cq = _np(_cuda(np.ascontiguousarray(col)).to(dtype)).astype(np.float64)
+        want = np.einsum("nhwk,nkc->nchw", d, cq[:, : m + 1])
+        img, comp = ops.render_preview(b["xs"], b["ys"], b["covs"], b["sizes"], _cuda(colors).to(dtype), h, w, want_composed=True)
+        assert img.shape == (n, 3, h, w) and img.dtype == dtype
+        close_scaled(_np(img), want, rel, f"preview {n}x{m}x{h}x{w}")
+        close_scaled(_np(comp), np.moveaxis(d, -1, 1), rel, "preview composed")
+    # through the reference-signature API: the UI call (blobctrl_app.py:637-646) takes the one-launch path
+    blob = blob_oracle.blob_from_ellipse(G.ellipses()[12]["ellipse"], 512, 512)
+    bb = {k: _cuda(v).to(dtype) if k != "sizes" else _cuda(v) for k, v in blob.items()}
+    got = U.get_blob_vis_img_from_blob_dict(bb, viz_size=(128, 128))
+    d2, _ = ops.render_scores(bb["xs"], bb["ys"], bb["covs"], bb["sizes"], 128, 128)
+    three = ops.feature_splat(d2, U.BLOB_VIS_COLORS[:2][None].to(DEV).to(dtype), engine="fma")
+    assert got.dtype == dtype and (got - three).abs().max().item() <= (1e-6 if dtype == torch.float32 else 1e-14)
+
+
+def test_graphed_preview_back_to_back_without_sync():
+    """consecutive GraphedBlobRenderer calls with no synchronisation between them must each render their own
+    parameters (the pinned staging block is double-buffered behind an event)."""
+    from blobctrl_b200.preview import preview_renderer
+    U = _impl()
+    r = preview_renderer((96, 96), DEV)
+    idxs = [1, 12, 30, 5, 20, 33, 8]
+    blobs = [blob_oracle.blob_from_ellipse(G.ellipses()[i]["ellipse"], 512, 512) for i in idxs]
+    snaps = []
+    for b in blobs:                                        # no sync between calls; snapshot in stream order
+        _, img = r(b["xs"], b["ys"], b["covs"])
+        snaps.append(img.clone())
+    torch.cuda.synchronize()
+    for b, img in zip(blobs, snaps):
+        b32 = {k: _cuda(v).float() for k, v in b.items()}
+        want = U.get_blob_vis_img_from_blob_dict(b32, viz_size=(96, 96))
+        assert (img - want).abs().max().item() <= 2e-6
+
+
+def test_cuda_graph_kwarg_replays_and_tracks_in_place_updates():
+    """splat_features(..., cuda_graph=True): same values as the eager call; a second call with the same tensors is a replay
+    that sees in-place parameter updates; a different shape captures its own graph."""
+    from blobctrl_b200 import graphs
+    U = _impl()
+    graphs.clear()
+    syn = blob_oracle.synthetic_blobs(1, 16, seed=3, c=320)
+    b = _blob(syn); f = _cuda(syn["features"])
+    eager = U.splat_features(**b, features=f, score_size=64, interp_size=64, ret_layout=False)
+    g1 = U.splat_features(**b, features=f, score_size=64, interp_size=64, ret_layout=False, cuda_graph=True)
+    assert torch.equal(g1["feature_grid"], eager["feature_grid"]) and torch.equal(g1["scores_pyramid"][64], eager["scores_pyramid"][64])
+    syn2 = blob_oracle.synthetic_blobs(1, 16, seed=4, c=320)
+    for k in ("xs", "ys", "covs", "sizes"):
+        b[k].copy_(_cuda(syn2[k]))
+    f.copy_(_cuda(syn2["features"]))
+    g2 = U.splat_features(**b, features=f, score_size=64, interp_size=64, ret_layout=False, cuda_graph=True)
+    eager2 = U.splat_features(**b, features=f, score_size=64, interp_size=64, ret_layout=False)
+    assert g2["feature_grid"].data_ptr() == g1["feature_grid"].data_ptr()          # a replay into the static buffers
+    assert torch.equal(g2["feature_grid"], eager2["feature_grid"])
+    one = blob_oracle.blob_from_ellipse(G.ellipses()[3]["ellipse"], 512, 512)
+    o32 = {k: _cuda(v).float() for k, v in one.items()}
+    d = U.splat_features(**o32, score_size=(128, 128), return_d_score=True, cuda_graph=True)
+    assert torch.equal(d, U.splat_features(**o32, score_size=(128, 128), return_d_score=True))
+    graphs.clear()
+
+
+def test_cuda_failure_propagates_unsupported_falls_back(monkeypatch):
+    """a -3 status (CUDA failure) from the fused render must reach the caller; only -2 (outside the
+    kernel's envelope, nothing launched) selects another engine."""
+    from blobctrl_b200 import _capi, ops
+    U = _impl()
+    syn = blob_oracle.synthetic_blobs(2, 16, seed=5, c=64)
+    b = _blob(syn); f = _cuda(syn["features"])
+    want = U.splat_features(**b, features=f, score_size=16, interp_size=16, ret_layout=False, engine="fma")["feature_grid"]
+
+    def boom(*a, **k):
+        raise _capi.BlobSplatCudaError("blobsplat: CUDA failure (status -3): injected")
+    monkeypatch.setattr(ops, "render_fused", boom)
+    with pytest.raises(_capi.BlobSplatCudaError):
+        U.splat_features(**b, features=f, score_size=16, interp_size=16, ret_layout=False)
+    with pytest.raises(_capi.BlobSplatCudaError):
+        U.splat_features_multiscale(**b, score_size=16, level_features={16: f, 8: f})
+
+    def unsupported(*a, **k):
+        raise _capi.BlobSplatUnsupported("blobsplat: unsupported: injected")
+    monkeypatch.setattr(ops, "render_fused", unsupported)
+    got = U.splat_features(**b, features=f, score_size=16, interp_size=16, ret_layout=False)["feature_grid"]
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    # the real library reports -2 for a shape outside the tensor kernel (no launch), and the message says so
+    with pytest.raises(_capi.BlobSplatUnsupported, match="unsupported"):
+        ops.feature_splat(torch.rand(1, 130, 8, 8, device=DEV), torch.randn(1, 130, 64, device=DEV), engine="tensor")
+
+
+def test_pipeline_method_fixtures_on_the_cuda_path():
+    """a10 against fixtures recorded from the reference's own StableDiffusionBlobNetPipeline methods
+    (tests/golden/make_golden_pipeline.py; pipeline_blobnet.py:706-739, :973-984), float16 and float32."""
+    import json
+    import os
+    from blobctrl_b200.pipelines import (BlobConditioningMixin, BlobNetInputBuffers, construct_blobnet_input,
+                                         prepare_blob_conditioning)
+    z = np.load(os.path.join(G.GOLDEN, "pipeline.npz"))
+    mix = BlobConditioningMixin()
+    for c in json.load(open(os.path.join(G.GOLDEN, "pipeline_cases.json")))["cases"]:
+        n = c["name"]
+        if c["func"] == "splat_features_from_scores":
+            sc, ft = _cuda(z[f"{n}/scores"]), _cuda(z[f"{n}/features"])
+            got = mix.splat_features_from_scores(sc, ft, c["size"], channels_last=c["channels_last"])
+            want = z[f"{n}/out"]
+            assert got.dtype == sc.dtype and got.is_contiguous()
+            rel = 2e-3 if sc.dtype == torch.float16 else 1e-5
+            close_scaled(_np(got[:, ::c["c_stride"]]), want.astype(np.float64), rel, n)
+            if sc.shape[1 if not c["channels_last"] else 3] == 1 and sc.dtype == torch.float16:
+                # K = 1 in 16 bits: one exact product, one rounding -> bit-identical to the reference's einsum
+                assert np.array_equal(_np(got[:, ::c["c_stride"]]), want.astype(np.float32)), n
+        elif c["func"] == "construct_blobnet_input":
+            t = {k: _cuda(z[f"{n}/{k}"]) for k in ("lat", "img", "scores", "feats", "fg", "bg")}
+            assert torch.equal(mix.construct_blobnet_input(t["lat"], t["scores"], t["img"], t["feats"]), t["fg"])
+            assert torch.equal(construct_blobnet_input(t["lat"], t["scores"], t["img"], background=True), t["bg"])
+        else:                                              # the prologue :973-984 + one step's canvases
+            gs = _cuda(z[f"{n}/gs_score"]); dino = _cuda(z[f"{n}/dino"])
+            dt = dino.dtype
+            cond = prepare_blob_conditioning(gs, dino, batch=c["batch"], dtype=dt, device=DEV)
+            want_f = z[f"{n}/fg_gs_feats"]
+            if dt == torch.float16:
+                assert np.array_equal(_np(cond.fg_gs_feats), want_f.astype(np.float32)), n
+            else:
+                close_scaled(_np(cond.fg_gs_feats), want_f.astype(np.float64), 1e-5, n)
+            lat, fg_lat, bg_lat = (_cuda(z[f"{n}/{k}"]) for k in ("lat", "fg_lat", "bg_lat"))
+            x = construct_blobnet_input(lat, cond.fg_gs_scores, fg_lat, cond.fg_gs_feats)
+            xb = construct_blobnet_input(lat, cond.bg_gs_scores, bg_lat, background=True)
+            want_x, want_xb = _cuda(z[f"{n}/blobnet_model_input"]), _cuda(z[f"{n}/unet_bg_input"])
+            assert torch.equal(xb, want_xb)
+            bufs = BlobNetInputBuffers(c["batch"], lat.shape[2], lat.shape[3], dino.shape[-1], dt, DEV)
+            bufs.fill_static(cond.fg_gs_scores, cond.bg_gs_scores, dino.repeat(c["batch"], 1, 1), fg_lat, bg_lat)
+            px, pxb = bufs.update(lat)
+            assert torch.equal(pxb, want_xb) and torch.equal(px, x)
+            if dt == torch.float16:
+                assert torch.equal(x, want_x), n
+            else:
+                close_scaled(_np(x), _np(want_x).astype(np.float64), 1e-5, n)
+
+
+@pytest.mark.parametrize("dtype,rel", [(torch.float32, 1e-5), (torch.float16, 2e-3), (torch.bfloat16, 1e-2)])
+def test_hoisted_conv_in_kernels_equal_the_full_convolution(dtype, rel):
+    """N1 on the GPU: blobsplat_conv_in_weights + blobsplat_conv_in_hoisted == conv_in over the (4 + 1 + C)-plane canvas of
+    construct_blobnet_input (models/blobnet.py:241-245, :840; pipeline_blobnet.py:724-739), K = 1 as the pipeline runs it
+    and rank-K conditioning, against a float64 convolution of the reference canvas."""
+    from blobctrl_b200.pipelines import HoistedConvIn, construct_blobnet_input
+    g = torch.Generator().manual_seed(0)
+    for (b2, h, w, c, o, k) in [(2, 12, 12, 20, 8, 1), (3, 16, 16, 1024, 320, 1), (2, 9, 20, 33, 40, 3), (1, 64, 64, 64, 64, 5)]:
+        weight = (torch.randn(o, 4 + 1 + c, 3, 3, generator=g) * (9 * (5 + c)) ** -0.5).to(DEV).to(dtype)
+        bias = torch.randn(o, generator=g).to(DEV).to(dtype)
+        score = torch.rand(b2, 1, h, w, generator=g).to(DEV).to(dtype)
+        sk = score if k == 1 else torch.rand(b2, k, h, w, generator=g).to(DEV).to(dtype)
+        f = torch.randn(b2, k, c, generator=g).to(DEV).to(dtype)
+        img_lat = torch.randn(b2, 4, h, w, generator=g).to(DEV).to(dtype)
+        hoist = HoistedConvIn(weight, bias)
+        hoist.prepare(score, sk, f)
+        feats64 = torch.einsum("nkhw,nkc->nchw", sk.double(), f.double())
+        for _ in range(2):
+            lat = torch.randn(b2, 4, h, w, generator=g).to(DEV).to(dtype)
+            canvas = construct_blobnet_input(lat.double(), score.double(), img_lat.double(), feats64)
+            want = torch.nn.functional.conv2d(canvas, weight.double(), bias.double(), padding=1)
+            got = hoist(torch.cat([img_lat, lat], dim=-1))
+            assert got.shape == want.shape == (b2, o, h, 2 * w) and got.dtype == dtype
+            close_scaled(_np(got), _np(want), rel, f"hoisted conv_in B={b2} C={c} O={o} K={k}")
+    # the layer as the reference runs it (full canvas in, library convolution): same module, untouched semantics
+    full = construct_blobnet_input(lat, score, img_lat, torch.einsum("nkhw,nkc->nchw", sk.float(), f.float()).to(dtype))
+    assert hoist(full).shape == (b2, o, h, 2 * w)
+
+
+def test_residual_injection_accepts_the_pipelines_cropped_views():
+    """pipeline_blobnet.py:1085-1087 passes ``residual[..., -h:]`` (a strided view): consumed in place, same bits."""
+    from blobctrl_b200.pipelines import inject_residual
+    g = torch.Generator().manual_seed(12)
+    for dtype in (torch.float16, torch.float32):
+        hidden = torch.randn(3, 10, 8, 16, generator=g).to(DEV).to(dtype)
+        res = torch.randn(3, 10, 8, 16, generator=g).to(DEV).to(dtype)
+        crop = res[..., -8:]
+        assert not crop.is_contiguous()
+        want = hidden.clone(); want[..., -8:] = want[..., -8:] + crop
+        assert torch.equal(inject_residual(hidden.clone(), crop, 1.0), want)
+        odd = res[:, :, :, 3:11]                           # not the right-most columns: falls back to a contiguous copy
+        want2 = hidden.clone(); want2[..., -8:] = want2[..., -8:] + odd
+        assert torch.equal(inject_residual(hidden.clone(), odd, 1.0), want2)
+
+
+def _have_reference():
+    import os
+    return os.path.isdir(os.path.join(os.path.dirname(G.HERE), "baseline", "_ref", "blobctrl"))
+
+
+@pytest.mark.skipif(not _have_reference(), reason="baseline/_ref not installed (scripts/install_reference.sh)")
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_cfg4_edit_loop_latent_parity_toy_width(dtype):
+    """BASELINE configs[3] at toy width: the UNMODIFIED reference pipeline loop (pipeline_blobnet.py:1024-1102) vs the same
+    object with the CUDA splat, persistent canvases (N2), hoisted conv_in (N1) and hooked residual injection (N4).
+    N2 + N4 are bit-exact substitutions; N1 re-associates one convolution (<= 1e-2 of the latent scale in 16 bits)."""
+    from baseline import cfg4_harness as H
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    r = H.compare_arms(device=DEV, dtype=dtype, batch=2, steps=6, small=True, warm_steps=1)
+    assert np.isfinite(r["latent_absmax"]) and r["gs_score_max_abs_diff"] <= 1e-5
+    a, b = r["ours_n2_n4"], r["ours_n1_n2_n4"]
+    # toy UNet: conv_in + (1 pair + downsampler) + 1 resnet | mid | (2 resnets + upsampler) + 2 pairs = 10 residuals per step
+    assert a["calls"]["injections"] == 6 * 10 and a["calls"]["splat_calls"] == 1 and a["calls"]["canvas_fills"] == 2
+    assert a["calls"]["canvas_updates"] == 12
+    assert a["latent_rel_to_absmax"] <= (1e-4 if dtype == torch.float32 else 1e-2), a
+    assert b["latent_rel_to_absmax"] <= (1e-3 if dtype == torch.float32 else 1e-2), b
