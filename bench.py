@@ -14,10 +14,17 @@ feature grid [N,320,64,64].
   value      whole-job Mpixel*blob/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e        same metric through the public host-input API (blobctrl_b200.streaming.HostRenderer) with HOST
              (pinned) inputs: chunked H2D of parameters and features overlapped with the render, and a D2H
-             read-back of the last image's maps, all inside the timed region
-  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs MEASURED_PEAKS hbm_gbs
-  cpu_baseline  the reference's PyTorch-CPU op sequence (oracle/aten_port.py — /root/reference cannot
-             travel to the GPU box) timed on the host cores on a bounded sample of the same workload
+             read-back of the last image's maps (a SAMPLE of the result: the maps are consumed on the device by
+             BlobNet/UNet), all inside the timed region.  e2e.full_d2h is the same step with the WHOLE 6.46 GB
+             result copied back, measured once beside it; e2e.h2d_probe is the raw aggregated pinned-H2D rate of the
+             same bytes (the host link's ceiling at this N).
+  roofline   dominant kernel: algorithmic bytes per launch / its CUDA-event duration vs MEASURED_PEAKS hbm_gbs;
+             roofline.sustained is the same step back to back for >= 2 s (settled clocks), with its own frac
+  cpu_baseline  the UNMODIFIED reference renderer (baseline/_ref, installed by scripts/install_reference.sh; kind
+             "reference") — or, when that is absent, the reference's PyTorch-CPU op sequence restated in
+             oracle/aten_port.py (kind "port") — timed on the host cores on a bounded sample of the same workload
+  strong / gather (N > 1)  BASELINE configs[4] literally: 1024 images in total, 1024/N per rank; and the optional
+             final NCCL all-gather of the maps (sharding.gather_maps), timed separately, never inside `value`
 """
 import argparse
 import json
@@ -117,17 +124,32 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the reference's PyTorch-CPU renderer (ATen port), bounded sample
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_rate(sample_images, reps, threads):
+def reference_renderer():
+    """(run(blobs, feats), kind): the unmodified reference from baseline/_ref when installed, else the ATen port."""
+    try:
+        from baseline import ref_loader
+        if ref_loader.available():
+            U = ref_loader.load(need_pipeline=False).utils
+            return (lambda blobs, feats: U.splat_features(**blobs, features=feats, score_size=SIZE, interp_size=SIZE,
+                                                          ret_layout=False)), "reference"
+    except Exception as e:  # pragma: no cover
+        print(f"bench: baseline/_ref unusable ({e}); falling back to the ATen port", file=sys.stderr)
     from oracle import aten_port            # test infrastructure: allowed here as the timed CPU baseline only
+    return (lambda blobs, feats: aten_port.render(**blobs, features=feats, score_size=SIZE, interp_size=SIZE,
+                                                  ret_layout=False)), "port"
+
+
+def cpu_reference_rate(sample_images, reps, threads):
+    render, kind = reference_renderer()
     torch.set_num_threads(threads)
     blobs, feats = synthetic(sample_images, M_BLOBS, CHANNELS, seed=0)
-    run = lambda: aten_port.render(**blobs, features=feats, score_size=SIZE, interp_size=SIZE, ret_layout=False)
+    run = lambda: render(blobs, feats)
     run()                                    # warm-up
     times = []
     for _ in range(reps):
         t0 = time.perf_counter(); run(); times.append(time.perf_counter() - t0)
     pxb = sample_images * M_BLOBS * SIZE * SIZE
-    return pxb / min(times) / 1e6, pxb / statistics.median(times) / 1e6, times
+    return pxb / min(times) / 1e6, pxb / statistics.median(times) / 1e6, times, kind
 
 
 def run_reference_arm(args):
@@ -137,9 +159,9 @@ def run_reference_arm(args):
     threads = os.cpu_count() or 1
     sample = 32
     blobs, feats = synthetic(sample, M_BLOBS, CHANNELS, seed=0)
-    from oracle import aten_port
+    render, kind = reference_renderer()
     torch.set_num_threads(threads)
-    run = lambda: aten_port.render(**blobs, features=feats, score_size=SIZE, interp_size=SIZE, ret_layout=False)
+    run = lambda: render(blobs, feats)
     for _ in range(max(args.warmup, 1)):
         run()
     t0 = time.perf_counter()
@@ -154,10 +176,12 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference's PyTorch-CPU op sequence (oracle/aten_port.py; bit-identical to /root/reference on the "
-                "golden fixtures) on the host cores; the reference tree itself cannot travel to the GPU box",
+        "note": ("the UNMODIFIED reference renderer (blobctrl/utils/utils.py::splat_features, pip-installed into baseline/_ref) "
+                 "on the host cores" if kind == "reference" else
+                 "reference's PyTorch-CPU op sequence (oracle/aten_port.py; bit-identical to /root/reference on the golden "
+                 "fixtures) on the host cores; baseline/_ref was not installed"),
     }))
     return 0
 
@@ -167,8 +191,10 @@ def workload_config(n_gpus):
                         f"(BASELINE.json configs[4]; largest single-GPU config)",
             "images_per_gpu": N_IMG, "blobs": M_BLOBS, "size": SIZE, "channels": CHANNELS, "sharding": f"by-image x{n_gpus}",
             "l2": "outputs 6.5 GB/step stream through the 126 MB L2 (>> L2); the 87 MB of inputs are re-read each step",
-            "e2e_pipeline": "HostRenderer: pinned H2D in 4 chunks on a copy stream, double-buffered staging (the copies of "
-                            "step i+1 overlap the renders of step i), D2H of the last image's maps every step"}
+            "e2e_pipeline": "H2D + render + sample D2H — HostRenderer: pinned H2D in 4 chunks on a copy stream, double-buffered "
+                            "staging (the copies of step i+1 overlap the renders of step i), D2H of the LAST IMAGE's maps every "
+                            "step (6.3 MB of the 6.46 GB result; the maps are consumed on the device).  e2e.full_d2h copies the "
+                            "whole result back instead"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -187,6 +213,49 @@ def time_steps(fn, steps, warmup, barrier):
     return e0.elapsed_time(e1) / 1e3   # seconds for `steps` steps
 
 
+def kernel_source_sha():
+    """Hash of the sources the dominant kernel is built from: ties a committed ncu traffic figure to the running build."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "blobctrl_b200", "csrc")
+    for f in ("common.cuh", "render_tc.cuh", "render_tc2.cuh", "render_tc.cu"):
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full summary
+    (profiles/traffic.json, written by scripts/ncu_summary.py) — only when it was captured on THIS build of the kernel
+    at THIS shape; otherwise null (a stale number is worse than none)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "no profiles/traffic.json"
+    for e in t.get("entries", []):
+        if (kernel_name.startswith(e.get("kernel_prefix", "?")) and e.get("csrc_sha16") == kernel_source_sha()
+                and e.get("shape") == {"N": N_IMG, "M": M_BLOBS, "S": SIZE, "C": CHANNELS, "dtype": "f32"}):
+            return int(e["dram_bytes_read"] + e["dram_bytes_write"]), f"profiles/traffic.json ({e.get('capture', '?')})"
+    return None, "profiles/traffic.json has no capture of this build/shape"
+
+
+def run_for(fn, seconds, barrier):
+    """fn back to back for >= `seconds` of device time: (ms per call, calls).  Clocks settle under sustained load."""
+    torch.cuda.synchronize(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    calls, batch = 0, 50
+    e0.record()
+    t0 = time.perf_counter()
+    while True:
+        for _ in range(batch):
+            fn()
+        calls += batch
+        torch.cuda.synchronize()
+        if time.perf_counter() - t0 >= seconds:
+            break
+    e1.record(); torch.cuda.synchronize(); barrier()
+    return e0.elapsed_time(e1) / calls, calls
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,6 +264,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -212,6 +283,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if dist else (lambda: None)
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        if dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
 
     import blobctrl_b200 as B
     from blobctrl_b200 import ops
@@ -249,10 +326,23 @@ def main():
         e2e_total = time_steps(e2e_step, args.steps, args.warmup, barrier)
     clocks = clk.summary()
 
-    t = torch.tensor([total, e2e_total], device=dev, dtype=torch.float64)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total, e2e_total = t.tolist()
+    # ---- the host link's ceiling at this N: the same H2D bytes, all ranks at once, nothing else running -------------
+    stage = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}
+    stage_f = torch.empty_like(pin_feats, device=dev)
+
+    def h2d_only():
+        for k, v in pin.items():
+            stage[k].copy_(v, non_blocking=True)
+        stage_f.copy_(pin_feats, non_blocking=True)
+    h2d_total = time_steps(h2d_only, args.steps, 3, barrier)
+    del stage, stage_f
+
+    # ---- sustained: the same device-resident step back to back for >= 2 s (clocks settle, power state ramps) -------
+    with ClockSampler(local) as sclk:
+        sus_ms, sus_calls = run_for(step, args.sustained_seconds, barrier)
+    sus_clocks = sclk.summary()
+
+    total, e2e_total, h2d_total, sus_ms = max_over_ranks(total, e2e_total, h2d_total, sus_ms)
     pxb_step = N_IMG * M_BLOBS * P * world
     value = pxb_step * args.steps / total / 1e6
     e2e_value = pxb_step * args.steps / e2e_total / 1e6
@@ -260,40 +350,112 @@ def main():
     d2h = out_host.numel() * 4
 
     peak, peak_src = peaks()
+    step_bytes = algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4)
     dom = max(kern, key=lambda k: k["ms"])
+    traffic, traffic_src = measured_traffic(dom["name"])
     roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": peak,
             "unit": "GB/s", "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel at this shape, from the
-            # ncu --set full capture summarised in profiles/render_tc_r1.md (0.0872 GB read + 6.4000 GB written)
-            "traffic": 6486408992 if dom["name"].startswith("render_tc") else None,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel_source_sha16": kernel_source_sha(),
             "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["ms"],
-            "step_alg_bytes": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4),
-            "step_frac": algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4) / (total / args.steps) / 1e9 / peak,
+            "step_alg_bytes": step_bytes, "step_frac": step_bytes / (total / args.steps) / 1e9 / peak,
+            "sustained": {"seconds": args.sustained_seconds, "steps": sus_calls, "ms_per_step": sus_ms,
+                          "achieved": step_bytes / (sus_ms * 1e-3) / 1e9, "frac": step_bytes / (sus_ms * 1e-3) / 1e9 / peak,
+                          "value": pxb_step / (sus_ms * 1e-3) / 1e6, "clocks": sus_clocks,
+                          "note": "same step as `value`, back to back for >= the stated seconds; max over ranks"},
             "kernels": kern}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_total / args.steps * 1e3},
+                    "ms_per_step": e2e_total / args.steps * 1e3,
+                    "what": "H2D of all inputs + render + D2H of the last image's maps (a sample of the result)",
+                    "h2d_probe": {"ms_per_step": h2d_total / args.steps * 1e3,
+                                  "aggregate_GBs": h2d * world / (h2d_total / args.steps) / 1e9,
+                                  "per_gpu_GBs": h2d / (h2d_total / args.steps) / 1e9,
+                                  "note": "raw pinned H2D of one step's inputs on every rank at once (max over ranks): the "
+                                          "floor of an e2e step at this N; the box is one NUMA node, 32 vCPUs"}},
             "gpu_launches": args.steps * len(kern), "roofline": roof, "clocks": clocks}
+
+    # ---- e2e with the WHOLE result copied back (once, few steps: 6.46 GB of pinned host memory) ---------------------
+    if rank == 0 and world == 1 and not args.no_variants:
+        try:
+            full = torch.empty((N_IMG, M_BLOBS + 1 + CHANNELS, SIZE, SIZE), dtype=torch.float32).pin_memory()
+
+            def e2e_full():
+                o = host_renderer(pin["xs"], pin["ys"], pin["covs"], pin["sizes"], pin_feats)
+                full[:, :M_BLOBS + 1].copy_(o["scores_pyramid"][SIZE], non_blocking=True)
+                full[:, M_BLOBS + 1:].copy_(o["feature_grid"], non_blocking=True)
+            t_full = time_steps(e2e_full, 3, 1, barrier)
+            line["e2e"]["full_d2h"] = {"value": pxb_step * 3 / t_full / 1e6, "ms_per_step": t_full / 3 * 1e3,
+                                       "d2h_bytes_per_step": full.numel() * 4,
+                                       "d2h_GBs": full.numel() * 4 / (t_full / 3) / 1e9, "steps": 3}
+            del full
+        except Exception as e:  # pragma: no cover
+            line["e2e"]["full_d2h"] = {"error": str(e)[:200]}
+
+    # ---- N > 1: strong scaling (BASELINE configs[4] literally) and the optional final gather, timed separately -----
+    if world > 1:
+        from blobctrl_b200.sharding import gather_maps, shard_bounds
+        lo, hi = shard_bounds(N_IMG, rank, world)
+        sb = {k: v[: hi - lo].contiguous() for k, v in blobs.items()}
+        sf = feats[: hi - lo].contiguous()
+
+        def strong_step():
+            return B.splat_features(**sb, features=sf, score_size=SIZE, interp_size=SIZE, ret_layout=False)
+        t_strong = time_steps(strong_step, args.steps, args.warmup, barrier)
+        with ClockSampler(local):
+            strong_sus, _ = run_for(strong_step, 1.0, barrier)
+        o = strong_step()
+        maps = torch.cat([o["scores_pyramid"][SIZE], o["feature_grid"]], 1)      # [N/G, 65 + 320, 64, 64]
+        del o
+        gather_maps(maps, N_IMG); torch.cuda.synchronize()
+        t_gather = time_steps(lambda: gather_maps(maps, N_IMG), 5, 2, barrier)
+        t_strong, strong_sus, t_gather = max_over_ranks(t_strong, strong_sus, t_gather)
+        gbytes = maps.numel() * 4 * world
+        line["strong"] = {"images_total": N_IMG, "images_per_gpu": hi - lo, "ms_per_step": t_strong / args.steps * 1e3,
+                          "value": N_IMG * M_BLOBS * P * args.steps / t_strong / 1e6,
+                          "sustained_ms_per_step": strong_sus, "sustained_value": N_IMG * M_BLOBS * P / (strong_sus * 1e-3) / 1e6,
+                          "note": "strong scaling: 1024 images in total; compare value with the N=1 line's value"}
+        line["gather"] = {"ms": t_gather / 5 * 1e3, "bytes_total": gbytes,
+                          "bus_GBs_per_gpu": gbytes * (world - 1) / world / (t_gather / 5) / 1e9,
+                          "what": "sharding.gather_maps: NCCL all_gather_into_tensor of the strong-scaling shard's maps "
+                                  "([1024/N, 385, 64, 64] fp32 per rank) to every rank; never inside `value`"}
+        del maps
 
     if rank == 0 and world == 1:
         if not args.no_variants:
             line["variants"] = variants(B, ops, dev, peak)
+            if not args.no_cfg4:
+                line["variants"]["cfg4_edit_loop"] = cfg4_variant()
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            best, med, times = cpu_reference_rate(256, 14, threads)
-            line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": "port", "median": med,
+            best, med, times, kind = cpu_reference_rate(256, 14, threads)
+            line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": threads, "kind": kind, "median": med,
                                     "sample": f"256 of {N_IMG} images (x{M_BLOBS} blobs, {SIZE}x{SIZE}, C={CHANNELS}, fp32), "
                                               f"best of 14 after 1 warm-up, {sum(times):.1f} s CPU wall"}
-            b1, _, t1 = cpu_reference_rate(8, 3, 1)
+            b1, _, t1, _ = cpu_reference_rate(8, 3, 1)
             line["cpu_baseline"]["single_thread"] = {"value": b1, "cores": 1, "sample": "8 images, best of 3"}
     if rank == 0:
         print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
     return 0
+
+
+def cfg4_variant():
+    """BASELINE configs[3]: the reference's 50-step edit loop (random-init SD-1.5 shapes, batch 8 -> 16 with CFG, fp16 +
+    autocast) stock vs with the CUDA splat / N1 / N2 / N4 substituted (baseline/cfg4_harness.py).  s/edit per arm, final
+    latent agreement, and the splat's measured share of an edit."""
+    try:
+        from baseline import cfg4_harness, ref_loader
+        if not ref_loader.available():
+            return {"unavailable": "baseline/_ref not installed (scripts/install_reference.sh needs /root/reference)"}
+        r = cfg4_harness.compare_arms(device="cuda", dtype=torch.float16, batch=8, steps=50)
+        torch.cuda.empty_cache()
+        return r
+    except Exception as e:  # pragma: no cover
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
 
 def probe_kernels(ops, blobs, feats, dev, reps):
@@ -375,23 +537,82 @@ def variants(B, ops, dev, peak):
     by = 64 * (28 * 32 + sum(33 * c * 2 + 33 * s * s * 2 + c * s * s * 2 for s, c in chans.items()))
     out["cfg3_multiscale_bf16"] = {"ms": ms, "Mpxblob_s": 64 * 32 * sum(s * s for s in chans) / ms / 1e3,
                                    "GBs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
-    # latency-bound configs: report microseconds
+    # latency-bound configs: report microseconds.  eager = the reference-signature call; graph = the same call with
+    # cuda_graph=True (one cudaGraphLaunch per call, blobctrl_b200/graphs.py); reference_* = the UNMODIFIED reference
+    # function (baseline/_ref) on the host CPU as its scripts run it, and its ~20-launch ATen sequence on this GPU
+    REF = None
+    try:
+        from baseline import ref_loader
+        if ref_loader.available():
+            REF = ref_loader.load(need_pipeline=False).utils
+    except Exception:  # pragma: no cover
+        REF = None
+
+    def cpu_us(fn, reps=5):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    lat = {}
     hb, hf = synthetic(1, 16, 320, seed=0)
     b2 = {k: v.to(dev) for k, v in hb.items()}; f2 = hf.to(dev)
-    out["cfg2_latency_us"] = 1e3 * timed(lambda: B.splat_features(**b2, features=f2, score_size=64, interp_size=64,
-                                                                   ret_layout=False), reps=50)
-    hb, _ = synthetic(1, 1, 1, seed=0)
-    b1 = {k: v.to(dev) for k, v in hb.items()}
-    out["cfg1_dscore_512_latency_us"] = 1e3 * timed(lambda: B.splat_features(**b1, score_size=(512, 512),
-                                                                              return_d_score=True), reps=50)
-    out["cfg1_viz_512_latency_us"] = 1e3 * timed(lambda: B.splat_features(
-        **b1, interp_size=64, viz_size=(512, 512), is_viz=True, score_size=64, viz_score_fn=B.viz_score_fn,
-        viz_colors=B.BLOB_VIS_COLORS, only_vis=True), reps=50)
-    # same preview as a CUDA graph over static buffers (host parameters in, one copy + one replay per call)
+    kw2 = dict(features=f2, score_size=64, interp_size=64, ret_layout=False)
+    lat["cfg2"] = {"eager_us": 1e3 * timed(lambda: B.splat_features(**b2, **kw2), reps=50),
+                   "graph_us": 1e3 * timed(lambda: B.splat_features(**b2, **kw2, cuda_graph=True), reps=200)}
+    hb1, _ = synthetic(1, 1, 1, seed=0)
+    b1 = {k: v.to(dev) for k, v in hb1.items()}
+    kwd = dict(score_size=(512, 512), return_d_score=True)
+    lat["cfg1_dscore_512"] = {"eager_us": 1e3 * timed(lambda: B.splat_features(**b1, **kwd), reps=50),
+                              "graph_us": 1e3 * timed(lambda: B.splat_features(**b1, **kwd, cuda_graph=True), reps=200)}
+    colors = B.BLOB_VIS_COLORS.to(dev)
+    kwv = dict(interp_size=64, viz_size=(512, 512), is_viz=True, score_size=64, viz_score_fn=B.viz_score_fn,
+               viz_colors=colors, only_vis=True)
+    lat["cfg1_viz_512"] = {"eager_us": 1e3 * timed(lambda: B.splat_features(**b1, **kwv), reps=50),
+                           "graph_us": 1e3 * timed(lambda: B.splat_features(**b1, **kwv, cuda_graph=True), reps=200)}
+    # the app's call shape: host numpy parameters in (blobctrl_app.py:604-646), one H2D copy + one graph replay per call
     from blobctrl_b200.preview import preview_renderer
     pr = preview_renderer((512, 512), dev)
-    hx, hy, hc = hb["xs"].numpy(), hb["ys"].numpy(), hb["covs"].numpy()
-    out["cfg1_viz_512_graph_latency_us"] = 1e3 * timed(lambda: pr(hx, hy, hc), reps=50)
+    hx, hy, hc = hb1["xs"].numpy(), hb1["ys"].numpy(), hb1["covs"].numpy()
+    lat["cfg1_viz_512"]["graph_host_params_us"] = 1e3 * timed(lambda: pr(hx, hy, hc), reps=100)
+    if REF is not None:
+        torch.set_num_threads(os.cpu_count() or 1)
+        c64 = {k: (v.double() if k != "sizes" else v) for k, v in hb1.items()}            # the scripts feed float64
+        kwv_cpu = dict(kwv, viz_colors=REF.BLOB_VIS_COLORS, viz_score_fn=REF.viz_score_fn)
+        lat["cfg1_viz_512"]["reference_cpu_f64_us"] = cpu_us(lambda: REF.splat_features(**c64, **kwv_cpu))
+        lat["cfg1_dscore_512"]["reference_cpu_f64_us"] = cpu_us(lambda: REF.splat_features(**c64, **kwd))
+        lat["cfg2"]["reference_cpu_f32_us"] = cpu_us(lambda: REF.splat_features(**hb, features=hf, score_size=64, interp_size=64,
+                                                                                 ret_layout=False))
+        try:    # the same reference code with its tensors on this GPU (device-agnostic torch ops)
+            kwv_gpu = dict(kwv, viz_colors=REF.BLOB_VIS_COLORS.to(dev), viz_score_fn=REF.viz_score_fn)
+            lat["cfg1_viz_512"]["reference_on_gpu_us"] = 1e3 * timed(lambda: REF.splat_features(**b1, **kwv_gpu), reps=20)
+            lat["cfg1_dscore_512"]["reference_on_gpu_us"] = 1e3 * timed(lambda: REF.splat_features(**b1, **kwd), reps=20)
+            lat["cfg2"]["reference_on_gpu_us"] = 1e3 * timed(lambda: REF.splat_features(**b2, **kw2), reps=20)
+            # and at the headline shape, 256-image chunks (its [N,M,2,P] intermediates are 0.5 GB each per chunk)
+            hbb, hff = synthetic(256, M_BLOBS, CHANNELS, seed=0)
+            bb = {k: v.to(dev) for k, v in hbb.items()}; ff = hff.to(dev)
+            ms = timed(lambda: REF.splat_features(**bb, features=ff, score_size=SIZE, interp_size=SIZE, ret_layout=False),
+                       reps=3, warm=1)
+            out["cfg5b_reference_on_gpu"] = {"ms_per_256_images": ms, "Mpxblob_s": 256 * M_BLOBS * P / ms / 1e3,
+                                             "what": "the unmodified reference splat_features with CUDA tensors on this B200 "
+                                                     "(ATen/cuSOLVER/cuBLAS kernels), 256-image chunk"}
+            del bb, ff
+        except Exception as e:  # pragma: no cover
+            lat["reference_on_gpu_error"] = f"{type(e).__name__}: {str(e)[:200]}"
+    out["latency"] = lat
+    # cfg3 as a CUDA graph (one launch of the captured call sequence)
+    try:
+        g3 = torch.cuda.CUDAGraph()
+        B.splat_features_multiscale(**blobs, score_size=64, level_features=lf, out_dtype=torch.bfloat16); torch.cuda.synchronize()
+        with torch.cuda.graph(g3):
+            keep = B.splat_features_multiscale(**blobs, score_size=64, level_features=lf, out_dtype=torch.bfloat16)
+        ms = timed(g3.replay, reps=50)
+        out["cfg3_multiscale_bf16"]["graph_ms"] = ms
+        out["cfg3_multiscale_bf16"]["graph_frac"] = by / ms / 1e6 / peak
+        del keep, g3
+    except Exception as e:  # pragma: no cover
+        out["cfg3_multiscale_bf16"]["graph_error"] = str(e)[:200]
     return out
 
 

@@ -870,6 +870,9 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   const long long whole_units = ctas > 0 ? (runs + ctas - 1) / ctas : 0;
   const long long whole = whole_units * ((long long)p.tiles_per_image * tw + BS_STAGE_COST);
   p.whole_runs = whole <= ranges ? 1 : 0;
+  if (const char* e = getenv("BLOBSPLAT_TC_SCHEDULE")) {      // A/B knob (read per call): "whole" | "ranges"
+    if (e[0] == 'w') p.whole_runs = 1; else if (e[0] == 'r') p.whole_runs = 0;
+  }
   // B ring + staging warps only where a CTA has enough units for staging to run ahead of; with one or two units per
   // CTA the 256 compute threads stage faster than the 96 staging threads and there is nothing to overlap with
   const long long units_per_cta = p.whole_runs ? whole_units : range_units;

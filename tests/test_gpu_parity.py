@@ -815,6 +815,7 @@ def test_cuda_failure_propagates_unsupported_falls_back(monkeypatch):
     def boom(*a, **k):
         raise _capi.BlobSplatCudaError("blobsplat: CUDA failure (status -3): injected")
     monkeypatch.setattr(ops, "render_fused", boom)
+    monkeypatch.setattr(ops, "render_multiscale", boom)
     with pytest.raises(_capi.BlobSplatCudaError):
         U.splat_features(**b, features=f, score_size=16, interp_size=16, ret_layout=False)
     with pytest.raises(_capi.BlobSplatCudaError):
@@ -823,6 +824,9 @@ def test_cuda_failure_propagates_unsupported_falls_back(monkeypatch):
     def unsupported(*a, **k):
         raise _capi.BlobSplatUnsupported("blobsplat: unsupported: injected")
     monkeypatch.setattr(ops, "render_fused", unsupported)
+    monkeypatch.setattr(ops, "render_multiscale", unsupported)
+    ms = U.splat_features_multiscale(**b, score_size=16, level_features={16: f, 8: f})
+    assert (ms["feature_grids"][16] - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     got = U.splat_features(**b, features=f, score_size=16, interp_size=16, ret_layout=False)["feature_grid"]
     assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     # the real library reports -2 for a shape outside the tensor kernel (no launch), and the message says so
