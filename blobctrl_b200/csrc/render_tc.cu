@@ -10,7 +10,7 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
   *why = "";
   if (out_dtype == BLOBSPLAT_F64 || feat_dtype == BLOBSPLAT_F64) { *why = "float64 runs on the FMA engine"; return 0; }
   if (feat_dtype != out_dtype) { *why = "features and maps must share a dtype"; return 0; }
-  const TcPlan pl = plan_tc(K, C, out_dtype == BLOBSPLAT_F32);
+  const TcPlan pl = plan_tc(K, C, split_of(out_dtype));
   if (!pl.ok) { *why = pl.why; return 0; }
   (void)H; (void)W;
   return 1;
@@ -20,7 +20,7 @@ int render_tc_dispatch(const float* xs, const float* ys, const float* covs, cons
                        int feat_dtype, int N, int M, int H, int W, int C, void* composed, void* grid, int out_dtype,
                        cudaStream_t st) {
   (void)feat_dtype;
-  const TcPlan pl = plan_tc(M + 1, C, out_dtype == BLOBSPLAT_F32);
+  const TcPlan pl = plan_tc(M + 1, C, split_of(out_dtype));
   if (!pl.ok) BS_UNSUPPORTED("fused render: %s", pl.why);
   RenderTcParams p{};
   p.xs = xs; p.ys = ys; p.covs = covs; p.sizes = sizes; p.feats = features; p.composed = composed; p.grid = grid;

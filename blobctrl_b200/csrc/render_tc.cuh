@@ -14,10 +14,16 @@
 //   D  fp32 accumulators in TMEM (C_tile <= 320 columns), split in two channel halves so the MMA of
 //      half h of tile t+1 overlaps the drain of the other half of tile t.
 //
-// Precision: float32 maps use the 3xTF32 split (hi = rna_tf32(x), lo = rna_tf32(x - hi);
-// D = Ahi*Bhi + Ahi*Blo + Alo*Bhi, fp32 accumulate) — product error ~3*2^-22, inside the 1e-5 parity
-// bar, at 1/3 of TF32 rate which still leaves the tensor pipe at ~50% of the HBM-bound tile time.
-// bf16/f16 maps use one kind::f16 MMA per k-step.
+// Precision (kSplit): float32 maps are split-precision MMAs with fp32 accumulation, two forms:
+//   kSplit = 2 (default)  2xFP16: x = x1 + x2, x1 = fp16(x), x2 = fp16(x - x1) for the weights and for the features (the
+//              features of a unit are first scaled by a power of two so that max|f| lands in [0.5, 1); the drain undoes it
+//              exactly).  D = A1*B1 + A1*B2 + A2*B1 under kind::f16: every product is exact in the fp32 accumulator, the
+//              dropped A2*B2 term and the fp16 subnormal resolution are <= 2^-24 of the unit's scale (measured ~2e-7).
+//              Three K16 MMAs per 16 blobs: 15 tensor instructions per half tile at K = 65 — 44% less tensor time than
+//              3xTF32, half the B footprint in shared memory (92 KB) and half the A columns in tensor memory.
+//   kSplit = 1            3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi); D = Ahi*Bhi + Ahi*Blo + Alo*Bhi — product
+//              error ~3*2^-22, 27 K8 MMAs per half tile.  Kept as the A/B partner (BLOBSPLAT_F32_SPLIT=tf32).
+// bf16/f16 maps (kSplit = 0) use one kind::f16 MMA per k-step.
 //
 // Warp roles (512 threads, 1 CTA/SM, persistent over work units = (image, channel chunk, tile range)):
 //   warps 0-7   stages 1+2 for one 128-pixel tile, two warps per TMEM lane quarter: each composites one
@@ -231,10 +237,14 @@ __device__ __forceinline__ void store_pair(OT* p0, OT* p1, float a, float b, boo
 
 // One 32-channel block of the pixel-pair epilogue (float maps): r[j] / r[16 + j] are channel j of this thread's two
 // adjacent pixels, stored as one 64-bit word; a half-warp covers one whole 128-byte line of a channel plane.
-__device__ __forceinline__ void store_pixel_pairs(float* oc, size_t P, const uint32_t* r, bool pred) {
+template <bool kScaled>
+__device__ __forceinline__ void store_pixel_pairs(float* oc, size_t P, const uint32_t* r, bool pred, float inv) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    if (pred) __stcs(reinterpret_cast<float2*>(oc + (size_t)j * P), make_float2(__uint_as_float(r[j]), __uint_as_float(r[16 + j])));
+  for (int j = 0; j < 16; ++j) {
+    float2 v = make_float2(__uint_as_float(r[j]), __uint_as_float(r[16 + j]));
+    if constexpr (kScaled) { v.x *= inv; v.y *= inv; }        // undo the unit's power-of-two feature scale (exact)
+    if (pred) __stcs(reinterpret_cast<float2*>(oc + (size_t)j * P), v);
+  }
 }
 
 struct RenderTcParams {
@@ -251,6 +261,7 @@ struct RenderTcParams {
   int whole_runs;         // schedule: whole (image, chunk) runs round-robin vs contiguous equal tile ranges
   int total_tiles;        // N * c_chunks * tiles_per_image, linear index ((n * c_chunks + chunk) * tiles_per_image + tile)
   int pair_ok;            // float maps: grid planes allow aligned 2-pixel stores (P even, base 8-byte aligned)
+  int tmem_cols;          // tensor-memory columns to allocate: accumulator + A operands, rounded up to a power of two
 };
 
 // First tile of CTA i's range under the equal-shares schedule.
@@ -270,20 +281,61 @@ struct RenderTcLevels {
 struct TcBarriers {
   uint64_t a_full, a_free, b_full[kTcMaxB], b_free[kTcMaxB], d_full[2], d_empty[2];
   uint32_t tmem_base;
+  float unit_inv[8];           // kSplit = 2: 1 / (power-of-two feature scale) of unit u in slot u & 7, applied by the drain.  8 slots:
+                               // a slot is rewritten 8 units later, by which time the drain has long read it (its d_empty arrivals
+                               // gate the MMAs of every unit in between)
+  float red[8];                // scratch of the staging threads' max reduction
 };
 
 // Stage one unit's B operand: features [K, C] (c contiguous) of image n, channels c0 .. c0 + c_tile - 1, into the K-major
 // no-swizzle operand layout at b_dst (second copy = TF32 residuals at + b_bytes).  Called by `nthreads` threads.
-template <typename FT, typename OT, bool kTf32>
+// kSplit = 2 additionally needs `sc` (TcBarriers: reduction scratch + the slot's inverse scale) and a named barrier shared by
+// exactly the calling threads.
+template <typename FT, typename OT, int kSplit>
 __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c0, unsigned char* b_smem, size_t b_bytes,
-                                           int tid, int nthreads) {
-  using BT = typename std::conditional<kTf32, float, OT>::type;
-  if constexpr (!kTf32 && BS_B_NMAJOR) {
+                                           int tid, int nthreads, TcBarriers* sc = nullptr, int slot = 0, int bar_id = 0) {
+  constexpr bool kTf32 = kSplit == 1;
+  constexpr bool kH2 = kSplit == 2;
+  using BT = typename std::conditional<kTf32, float, typename std::conditional<kH2, __half, OT>::type>::type;
+  float scale = 1.0f;
+  if constexpr (kH2) {
+    // power-of-two scale of this unit's features: max|f| * scale in [0.5, 1), so fp16's absolute resolution (2^-24) is
+    // relative to the unit's own magnitude whatever the features' range
+    const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
+    const int cw = min(p.c_tile, p.C - c0);
+    float mx = 0.0f;
+    if ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 3) == 0 && (cw & 3) == 0) {
+      const int q4 = cw >> 2;
+      for (int i = tid; i < p.K * q4; i += nthreads) {
+        const int k = i / q4, c = (i - k * q4) << 2;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(f + (size_t)k * p.C + c0 + c));
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+    } else {
+      for (int i = tid; i < p.K * cw; i += nthreads) {
+        const int k = i / cw, c = i - k * cw;
+        mx = fmaxf(mx, fabsf((float)__ldg(f + (size_t)k * p.C + c0 + c)));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((tid & 31) == 0) sc->red[tid >> 5] = mx;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    mx = 0.0f;
+    for (int w = 0; w < (nthreads >> 5); ++w) mx = fmaxf(mx, sc->red[w]);
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");      // scratch may be rewritten by the next unit
+    int e = 0;
+    if (mx > 0.0f && mx < 3.0e38f) (void)frexpf(mx, &e);                            // mx = m * 2^e, m in [0.5, 1)
+    e = max(-100, min(100, e));
+    scale = exp2f((float)-e);
+    if (tid == 0) sc->unit_inv[slot] = exp2f((float)e);
+  }
+  if constexpr (kSplit == 0 && BS_B_NMAJOR) {
     // 16-bit maps: B is an N-MAJOR operand (channels contiguous, as the features are stored) in the no-swizzle
     // canonical layout ((8 ch, 1, n), (8 k, groups)) : 8 k-rows x 16 bytes per core matrix, channel chunks 128 B
     // apart (SBO), k-groups c_tile*16 B apart (LBO).  Staging is a pure 16-byte copy, no conversion, no transposition:
     // item q = (k-group, channel chunk, row) goes to byte 16*q; a warp reads 8 feature rows x 64 contiguous bytes.
-    static_assert(kTf32 || (sizeof(FT) == 2 && std::is_same<FT, OT>::value), "16-bit staging copies raw elements");
+    static_assert(sizeof(FT) == 2 && std::is_same<FT, OT>::value, "16-bit staging copies raw elements");
     const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
     const int cq8 = p.c_tile >> 3;
     const int items = p.Kp * cq8;
@@ -353,6 +405,16 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
         for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j][cc]); lo[j] = rna_tf32(v[j][cc] - hi[j]); }
         *reinterpret_cast<float4*>(dst + cc * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(dst + cc * 16 + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      } else if constexpr (kH2) {
+        __half h1[8], h2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[j][cc] * scale;                    // exact: a power of two
+          h1[j] = __float2half_rn(x);
+          h2[j] = __float2half_rn(x - __half2float(h1[j]));
+        }
+        *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h1);
+        *reinterpret_cast<uint4*>(dst + cc * 16 + b_bytes) = *reinterpret_cast<const uint4*>(h2);
       } else {
         OT h[8];
 #pragma unroll
@@ -363,7 +425,8 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
   }
 }
 
-// FT: feature dtype in global memory; OT: output dtype; kTf32: 3xTF32 (float maps) vs kind::f16 (16-bit maps)
+// FT: feature dtype in global memory; OT: output dtype; kSplit: 0 = 16-bit maps (kind::f16), 1 = float maps by 3xTF32,
+// 2 = float maps by 2xFP16 (see the header)
 // kP: pixels per image when it is one of the common sizes (64^2, 32^2, 16^2), else 0 = runtime.  With a
 // compile-time plane stride every store of an unrolled group is [base + immediate]: no address arithmetic.
 // kP = -1: several pyramid levels in one launch (RenderTcLevels); every work unit reads its own level's shape.
@@ -371,18 +434,21 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
 // splat_features_from_scores) instead of being rendered from blob parameters (stages 1+2).
 // kRing: the CTA has the 3 staging warps and a ring of p.nb >= 2 B buffers; otherwise one buffer, staged by the compute
 // warps between units (the float path at BlobNet's sizes, where B fills shared memory, and launches with few units).
-template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores, bool kRing>
+template <typename FT, typename OT, int kSplit, int kHalves, int kP, bool kFromScores, bool kRing>
 __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32, 1) render_tc_kernel(const __grid_constant__ RenderTcLevels L) {
+  constexpr bool kTf32 = kSplit == 1;        // 3xTF32
+  constexpr bool kH2 = kSplit == 2;          // 2xFP16
+  constexpr bool kFloatMaps = kSplit != 0;   // float outputs: adjacent-pixel lane map, 64-bit pair stores
   const RenderTcParams& p0 = L.lv[0];     // Kp, c_tile and the dtypes are the same for every level
   if (threadIdx.x == 0) TC_STAMP(0);
   constexpr int kTcComputeWarps = 4 * kHalves;
   constexpr int kTcComputeThreads = kTcComputeWarps * 32;
   constexpr int kTcMmaWarp = kTcComputeWarps + 4;
   extern __shared__ __align__(1024) unsigned char smem[];
-  using BT = typename std::conditional<kTf32, float, OT>::type;   // element type of B in smem (tf32 bits or bf16/f16)
+  using BT = typename std::conditional<kTf32, float, typename std::conditional<kH2, __half, OT>::type>::type;   // B element in smem
   constexpr int kElemsPer16B = 16 / sizeof(BT);                    // T: 4 (tf32) or 8 (16-bit)
   constexpr int kKStep = 2 * kElemsPer16B;                         // K per MMA: 8 or 16
-  constexpr int kNumB = kTf32 ? 2 : 1;                             // hi + lo
+  constexpr int kNumB = kFloatMaps ? 2 : 1;                        // hi + lo / x1 + x2
   constexpr int kACols = kTf32 ? 1 : 2;                            // k elements per 32-bit TMEM column
 
   const int c_half = p0.c_tile >> 1;
@@ -409,7 +475,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"((uint32_t)p0.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -463,7 +529,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // Its pixel within the tile.  Float maps: lanes L and L+16 of a quarter hold ADJACENT pixels, so the epilogue's
       // 16x32bx2 TMEM loads hand one thread two consecutive pixels of a channel (64-bit stores, half the store
       // instructions).  A warp still covers the same 32 consecutive pixels, so the composed-map stores stay coalesced.
-      const int ppx = kTf32 ? q * 32 + ((lane & 15) << 1) + (lane >> 4) : px;
+      const int ppx = kFloatMaps ? q * 32 + ((lane & 15) << 1) + (lane >> 4) : px;
       asm volatile("bar.sync 1, %0;" ::"n"(kTcComputeThreads) : "memory");   // previous unit's tiles are done with `coef`
       // stage 3 from score maps: the planes of this warp, and the first tile's loads issued BEFORE the operand staging
       // so that the two global round trips of a unit's start overlap
@@ -493,7 +559,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       }
       if constexpr (!kRing) {   // single B buffer: staged here, after the MMAs of the previous unit have read it
         if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
-        tc_stage_b<FT, OT, kTf32>(p, n, c0, b_smem, b_bytes, ctid, kTcComputeThreads);
+        tc_stage_b<FT, OT, kSplit>(p, n, c0, b_smem, b_bytes, ctid, kTcComputeThreads, bars, unit_it & 7, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
         mbar_arrive(&bars->b_full[0]);
       }
@@ -636,6 +702,25 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             tmem_st8(tmem_a + lane_addr + g * 8, hi);
             tmem_st8(tmem_a + lane_addr + a_cols + g * 8, lo);
           }
+        } else if constexpr (kH2) {
+          // 2xFP16: w = w1 + w2 exactly to 2^-24; two k per 32-bit column, 8 columns = 16 consecutive k per operand
+          for (int g = half; g < p.Kp / 16; g += kHalves) {
+            uint32_t p1[8], p2[8];
+            const float* row = my - kTcKOff + g * 16;
+            const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
+            const float4 q2 = *reinterpret_cast<const float4*>(row + 8), q3 = *reinterpret_cast<const float4*>(row + 12);
+            const float wv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 h = __floats2half2_rn(wv[2 * j], wv[2 * j + 1]);
+              const float2 f = __half22float2(h);
+              const __half2 r = __floats2half2_rn(wv[2 * j] - f.x, wv[2 * j + 1] - f.y);
+              p1[j] = *reinterpret_cast<const uint32_t*>(&h);
+              p2[j] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+            tmem_st8(tmem_a + lane_addr + g * 8, p1);
+            tmem_st8(tmem_a + lane_addr + a_cols + g * 8, p2);
+          }
         } else {
           // two k per 32-bit column (low half = even k): 8 columns = 16 consecutive k
           for (int g = half; g < p.Kp / 16; g += kHalves) {
@@ -668,20 +753,22 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // ========================================= epilogue ==========================================
       const int q = warp - kTcComputeWarps;        // TMEM lane quarter
       OT* out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
+      float inv = 1.0f;                             // kSplit = 2: read once the unit's first accumulator has landed
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
         // same lane -> pixel map as stages 1+2
-        const int pix = (t_lo + t) * kTcTileM + q * 32 + (kTf32 ? ((lane & 15) << 1) + (lane >> 4) : lane);
+        const int pix = (t_lo + t) * kTcTileM + q * 32 + (kFloatMaps ? ((lane & 15) << 1) + (lane >> 4) : lane);
         const bool live = pix < P;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           mbar_wait(&bars->d_full[h], tile_it & 1);
           if (q == 0 && tile_it == 0) TC_STAMP(5 + h);   // first D half ready
           tc_fence_after();
+          if constexpr (kH2) { if (t == 0 && h == 0) inv = bars->unit_inv[unit_it & 7]; }   // staged before the unit's first MMA
           const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * c_half);
           OT* const o = out + (size_t)(h * c_half) * P + pix;   // this pixel in the half's first channel plane
           const int ch_left = p.C - (c0 + h * c_half);          // valid channels in this half (may exceed c_half)
           bool done = false;
-          if constexpr (kTf32) {
+          if constexpr (kFloatMaps) {
             if (p.pair_ok && ch_left >= c_half && (c_half & 31) == 0) {
               // float fast path: thread t owns pixels 2*(t%16), +1 of channels 16*(t/16) + j of each 32-channel block
               // (two 16-lane loads); the next block's loads are in flight while this one is stored
@@ -694,11 +781,11 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
               tmem_wait_ld();
               for (int cc = 0; cc < c_half; cc += 64) {
                 if (cc + 32 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 32, rb); tmem_ld_16x32bx2_x16(tb + cc + 32, rb + 16); }
-                store_pixel_pairs(o2 + (size_t)cc * P, (size_t)P, ra, live2);
+                store_pixel_pairs<kH2>(o2 + (size_t)cc * P, (size_t)P, ra, live2, inv);
                 tmem_wait_ld();
                 if (cc + 32 < c_half) {
                   if (cc + 64 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 64, ra); tmem_ld_16x32bx2_x16(tb + cc + 64, ra + 16); }
-                  store_pixel_pairs(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2);
+                  store_pixel_pairs<kH2>(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2, inv);
                   tmem_wait_ld();
                 }
               }
@@ -706,7 +793,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             }
           }
           if (done) {
-          } else if (!kTf32 && ch_left >= c_half && (c_half & 31) == 0) {
+          } else if (!kFloatMaps && ch_left >= c_half && (c_half & 31) == 0) {
             // 16-bit fast path: whole 32-column chunks, next TMEM load in flight while the current chunk is stored
             uint32_t ra[32], rb[32];
             tmem_ld32(taddr, ra);
@@ -736,7 +823,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
               tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (live && cc + j < ch_left) __stcs(o + (size_t)(cc + j) * P, Cvt<OT>::from(__uint_as_float(r[j])));
+                if (live && cc + j < ch_left) __stcs(o + (size_t)(cc + j) * P, Cvt<OT>::from(kH2 ? __uint_as_float(r[j]) * inv : __uint_as_float(r[j])));
             }
           }
           tc_fence_before();
@@ -748,8 +835,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // ========================================= MMA issue =========================================
       if (lane == 0) {
         const int buf = unit_it % nb, rnd = unit_it / nb;      // this unit's slot of the B ring
-        const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<OT, __half>::value ? 0u : 1u), (uint32_t)c_half,
-                                          (!kTf32 && BS_B_NMAJOR) ? 1u : 0u);
+        const uint32_t idesc = make_idesc(kTf32 ? 2u : (std::is_same<BT, __half>::value ? 0u : 1u), (uint32_t)c_half,
+                                          (kSplit == 0 && BS_B_NMAJOR) ? 1u : 0u);
         const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_stride);
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
         mbar_wait(&bars->b_full[buf], rnd & 1);
@@ -768,7 +855,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
               const uint32_t a_hi = tmem_a + (uint32_t)(ks * 8);
               if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi, b_hi, idesc, acc);
               acc = 1;
-              if constexpr (kTf32) {
+              if constexpr (kFloatMaps) {      // + Ahi*Blo + Alo*Bhi (3xTF32) / + A1*B2 + A2*B1 (2xFP16)
                 const uint64_t b_lo = make_b_desc(b_addr + (uint32_t)b_bytes, lbo, sbo);
                 if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi, b_lo, idesc, 1u);
                 if (!BS_ABL_NO_MMA) umma_ts<kTf32>(d_addr, a_hi + (uint32_t)a_cols, b_hi, idesc, 1u);
@@ -787,8 +874,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // have released it, so staging overlaps the tiles of the units before it
       const int buf = unit_it % nb, rnd = unit_it / nb;
       if (rnd > 0) mbar_wait(&bars->b_free[buf], (rnd - 1) & 1);
-      tc_stage_b<FT, OT, kTf32>(p, n, c0, b_smem + (size_t)buf * b_stride, b_bytes, (int)threadIdx.x - (kTcMmaWarp + 1) * 32,
-                                kTcStageWarps * 32);
+      tc_stage_b<FT, OT, kSplit>(p, n, c0, b_smem + (size_t)buf * b_stride, b_bytes, (int)threadIdx.x - (kTcMmaWarp + 1) * 32,
+                                 kTcStageWarps * 32, bars, unit_it & 7, 7);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
       mbar_arrive(&bars->b_full[buf]);
     }
@@ -803,7 +890,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   __syncthreads();
   if (threadIdx.x == 0) TC_STAMP(9);
   if (warp == kTcMmaWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p0.tmem_cols) : "memory");
   }
 }
 
@@ -811,17 +898,31 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
 // ---- host side ---------------------------------------------------------------------------------------
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct TcPlan { int Kp, c_tile, nb; size_t smem, b_slot; bool ok; const char* why; };   // smem = fixed part + nb * b_slot
+struct TcPlan { int Kp, c_tile, nb, tmem_cols; size_t smem, b_slot; bool ok; const char* why; };   // smem = fixed part + nb * b_slot
 
-static inline TcPlan plan_tc(int K, int C, bool tf32) {
+// float32 maps: which split-precision form (header of this file).  BLOBSPLAT_F32_SPLIT=tf32 selects 3xTF32 (A/B knob).
+static inline int f32_split() {
+  const char* e = getenv("BLOBSPLAT_F32_SPLIT");
+  return (e && e[0] == 't') ? 1 : 2;
+}
+static inline int split_of(int dtype) { return dtype == BLOBSPLAT_F32 ? f32_split() : 0; }
+
+static inline int tmem_cols_for(int needed) {
+  int c = 32;
+  while (c < needed) c <<= 1;
+  return c;
+}
+
+static inline TcPlan plan_tc(int K, int C, int split) {
   TcPlan pl{};
   pl.ok = false;
+  const bool tf32 = split == 1;
   const int kstep = tf32 ? 8 : 16;
   pl.Kp = round_up(K + kTcKOff, kstep);
   if (K - 1 > kTcMaxBlobs) { pl.why = "more than 127 blobs: use the FMA engine"; return pl; }
   if (C < 1) { pl.why = "no channels"; return pl; }
-  const int a_cols = tf32 ? 2 * pl.Kp : pl.Kp / 2;
-  const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : 2);                  // B bytes per channel (hi+lo fp32 | 16-bit)
+  const int a_cols = tf32 ? 2 * pl.Kp : (split == 2 ? pl.Kp : pl.Kp / 2);
+  const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : (split == 2 ? 4 : 2));   // B bytes per channel (hi+lo fp32 | x1+x2 fp16 | 16-bit)
   const size_t fixed = (size_t)(pl.Kp + 4) * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
   int c_tile = std::min(kTcMaxCTile, round_up(C, 32));     // any C: the last chunk may be ragged (zero B columns, predicated drain)
   c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
@@ -835,6 +936,7 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
   pl.nb = (int)std::min<size_t>(BS_MAX_B, (kTcSmemBudget - fixed) / (per_c * c_tile));
   pl.b_slot = per_c * c_tile;
   pl.smem = fixed + (size_t)pl.nb * pl.b_slot;
+  pl.tmem_cols = tmem_cols_for(c_tile + a_cols);
   pl.ok = true;
   return pl;
 }
@@ -843,6 +945,7 @@ static inline TcPlan plan_tc(int K, int C, bool tf32) {
 static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int H, int W, int C, int tile_px = kTcTileM) {
   p.N = N; p.M = K - 1; p.H = H; p.W = W; p.C = C; p.K = K; p.Kp = pl.Kp;
   p.c_tile = pl.c_tile; p.c_chunks = (C + pl.c_tile - 1) / pl.c_tile;
+  p.tmem_cols = pl.tmem_cols;
   const int P = H * W;
   p.tiles_per_image = (P + tile_px - 1) / tile_px;
   const long long total = (long long)N * p.c_chunks * p.tiles_per_image;
@@ -864,7 +967,7 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
     if (hi <= lo) continue;
     const int units = (hi - 1) / p.tiles_per_image - lo / p.tiles_per_image + 1;
     range_units = std::max(range_units, units);
-    ranges = std::max<long long>(ranges, (long long)(hi - lo) * tw + 2ll * BS_STAGE_COST * units);   // staggered stagings queue behind other CTAs' stores: twice the cost
+    ranges = std::max<long long>(ranges, (long long)(hi - lo) * tw + (long long)BS_STAGE_COST * units);   // weights fitted to profiles/schedule_ab_r2.txt
   }
   const long long runs = total / p.tiles_per_image;
   const long long whole_units = ctas > 0 ? (runs + ctas - 1) / ctas : 0;
@@ -881,13 +984,13 @@ static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int 
   return 0;
 }
 
-template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores, bool kRing>
+template <typename FT, typename OT, int kSplit, int kHalves, int kP, bool kFromScores, bool kRing>
 static int launch_tc_pr(const RenderTcParams& p, cudaStream_t st) {
   static thread_local int configured_dev = -1;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kSplit, kHalves, kP, kFromScores, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured_dev = dev;
   }
   static thread_local int sm_count = 0, sm_dev = -1;
@@ -901,30 +1004,30 @@ static int launch_tc_pr(const RenderTcParams& p, cudaStream_t st) {
   L.lv[0].pair_ok = ((p.H * p.W) & 1) == 0 && (reinterpret_cast<uintptr_t>(p.grid) & 7) == 0;
   L.n_levels = 1;
   L.tile_start[1] = p.total_tiles;
-  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kTf32, kHalves, kP, kFromScores, kRing>, dim3(grid),
+  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kSplit, kHalves, kP, kFromScores, kRing>, dim3(grid),
                      dim3((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)) * 32), (size_t)p.smem_bytes, st, L));
   return 0;
 }
 
-template <typename FT, typename OT, bool kTf32, int kHalves, int kP, bool kFromScores>
+template <typename FT, typename OT, int kSplit, int kHalves, int kP, bool kFromScores>
 static int launch_tc_p(const RenderTcParams& p, size_t, cudaStream_t st) {
   if constexpr (kHalves == 2) {
-    if (p.nb > 1) return launch_tc_pr<FT, OT, kTf32, kHalves, kP, kFromScores, true>(p, st);
+    if (p.nb > 1) return launch_tc_pr<FT, OT, kSplit, kHalves, kP, kFromScores, true>(p, st);
   }
-  return launch_tc_pr<FT, OT, kTf32, kHalves, kP, kFromScores, false>(p, st);
+  return launch_tc_pr<FT, OT, kSplit, kHalves, kP, kFromScores, false>(p, st);
 }
 
-template <typename FT, typename OT, bool kTf32, int kHalves, bool kFromScores>
+template <typename FT, typename OT, int kSplit, int kHalves, bool kFromScores>
 static int launch_tc(const RenderTcParams& p, size_t smem, cudaStream_t st) {
   if constexpr (kHalves == 2) {   // plane-stride specialisations for BlobNet's latent resolutions (64/32/16)
     switch (p.H * p.W) {
-      case 64: if constexpr (kFromScores) return launch_tc_p<FT, OT, kTf32, kHalves, 64, kFromScores>(p, smem, st); else break;
-      case 4096: return launch_tc_p<FT, OT, kTf32, kHalves, 4096, kFromScores>(p, smem, st);
-      case 1024: return launch_tc_p<FT, OT, kTf32, kHalves, 1024, kFromScores>(p, smem, st);
-      case 256: return launch_tc_p<FT, OT, kTf32, kHalves, 256, kFromScores>(p, smem, st);
+      case 64: if constexpr (kFromScores) return launch_tc_p<FT, OT, kSplit, kHalves, 64, kFromScores>(p, smem, st); else break;
+      case 4096: return launch_tc_p<FT, OT, kSplit, kHalves, 4096, kFromScores>(p, smem, st);
+      case 1024: return launch_tc_p<FT, OT, kSplit, kHalves, 1024, kFromScores>(p, smem, st);
+      case 256: return launch_tc_p<FT, OT, kSplit, kHalves, 256, kFromScores>(p, smem, st);
     }
   }
-  return launch_tc_p<FT, OT, kTf32, kHalves, 0, kFromScores>(p, smem, st);
+  return launch_tc_p<FT, OT, kSplit, kHalves, 0, kFromScores>(p, smem, st);
 }
 
 // 8 compute warps (kHalves = 2) win for every dtype once the GPU settles at its sustained clocks
@@ -936,16 +1039,17 @@ static int launch_tc_dtype(const RenderTcParams& p, size_t smem, int out_dtype, 
     if (const char* e = getenv("BLOBSPLAT_TC_HALVES")) { if (e[0] == '1') halves = 1; }
   }
   if (out_dtype == BLOBSPLAT_F32) {
-    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<float, float, true, 1, kFromScores>(p, smem, st); }
-    return launch_tc<float, float, true, 2, kFromScores>(p, smem, st);
+    if (f32_split() == 1) return launch_tc<float, float, 1, 2, kFromScores>(p, smem, st);            // 3xTF32 (A/B partner)
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<float, float, 2, 1, kFromScores>(p, smem, st); }
+    return launch_tc<float, float, 2, 2, kFromScores>(p, smem, st);
   }
   if (out_dtype == BLOBSPLAT_BF16) {
-    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__nv_bfloat16, __nv_bfloat16, false, 1, kFromScores>(p, smem, st); }
-    return launch_tc<__nv_bfloat16, __nv_bfloat16, false, 2, kFromScores>(p, smem, st);
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__nv_bfloat16, __nv_bfloat16, 0, 1, kFromScores>(p, smem, st); }
+    return launch_tc<__nv_bfloat16, __nv_bfloat16, 0, 2, kFromScores>(p, smem, st);
   }
   if (out_dtype == BLOBSPLAT_F16) {
-    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__half, __half, false, 1, kFromScores>(p, smem, st); }
-    return launch_tc<__half, __half, false, 2, kFromScores>(p, smem, st);
+    if constexpr (!kFromScores) { if (halves == 1) return launch_tc<__half, __half, 0, 1, kFromScores>(p, smem, st); }
+    return launch_tc<__half, __half, 0, 2, kFromScores>(p, smem, st);
   }
   BS_UNSUPPORTED("tensor-core engine: unsupported dtype %d", out_dtype);
 }

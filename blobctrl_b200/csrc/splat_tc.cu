@@ -8,7 +8,7 @@ namespace blobsplat {
 
 int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_t sp, const void* feats, void* out,
                               int N, int K, int C, int H, int W, int dtype, cudaStream_t st) {
-  const TcPlan pl = plan_tc(K, C, dtype == BLOBSPLAT_F32);
+  const TcPlan pl = plan_tc(K, C, split_of(dtype));
   if (!pl.ok) BS_UNSUPPORTED("tensor-core feature splat: %s", pl.why);
   if (dtype == BLOBSPLAT_F64) BS_UNSUPPORTED("tensor-core feature splat: float64 runs on the FMA engine");
   RenderTcParams p{};
@@ -22,13 +22,13 @@ int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_
 }
 
 // Several stage-3 problems (pyramid levels) in one launch; L.lv[*] filled by fill_tc_units, equal Kp / c_tile / dtype.
-template <typename FT, typename OT, bool kTf32, bool kRing>
+template <typename FT, typename OT, int kSplit, bool kRing>
 static int launch_tc_levels_r(RenderTcLevels& L, size_t smem, cudaStream_t st) {
   static thread_local int configured_dev = -1, sm_count = 0;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc_kernel<FT, OT, kSplit, 2, -1, true, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured_dev = dev;
   }
@@ -42,21 +42,22 @@ static int launch_tc_levels_r(RenderTcLevels& L, size_t smem, cudaStream_t st) {
   L.tile_start[L.n_levels] = (int)total;
   if (total == 0) return 0;
   const int grid = (int)std::min<long long>(sm_count, total);
-  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kTf32, 2, -1, true, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
+  BS_CUDA(launch_pdl(render_tc_kernel<FT, OT, kSplit, 2, -1, true, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
                      smem, st, L));
   return 0;
 }
 
-template <typename FT, typename OT, bool kTf32>
+template <typename FT, typename OT, int kSplit>
 static int launch_tc_levels_t(RenderTcLevels& L, size_t smem, cudaStream_t st) {
-  return L.lv[0].nb > 1 ? launch_tc_levels_r<FT, OT, kTf32, true>(L, smem, st)
-                        : launch_tc_levels_r<FT, OT, kTf32, false>(L, smem, st);
+  return L.lv[0].nb > 1 ? launch_tc_levels_r<FT, OT, kSplit, true>(L, smem, st)
+                        : launch_tc_levels_r<FT, OT, kSplit, false>(L, smem, st);
 }
 
 static int launch_tc_levels(RenderTcLevels& L, size_t smem, int dtype, cudaStream_t st) {
-  if (dtype == BLOBSPLAT_F32) return launch_tc_levels_t<float, float, true>(L, smem, st);
-  if (dtype == BLOBSPLAT_BF16) return launch_tc_levels_t<__nv_bfloat16, __nv_bfloat16, false>(L, smem, st);
-  if (dtype == BLOBSPLAT_F16) return launch_tc_levels_t<__half, __half, false>(L, smem, st);
+  if (dtype == BLOBSPLAT_F32)
+    return f32_split() == 1 ? launch_tc_levels_t<float, float, 1>(L, smem, st) : launch_tc_levels_t<float, float, 2>(L, smem, st);
+  if (dtype == BLOBSPLAT_BF16) return launch_tc_levels_t<__nv_bfloat16, __nv_bfloat16, 0>(L, smem, st);
+  if (dtype == BLOBSPLAT_F16) return launch_tc_levels_t<__half, __half, 0>(L, smem, st);
   BS_UNSUPPORTED("tensor-core engine: unsupported dtype %d", dtype);
 }
 
@@ -70,7 +71,7 @@ int feature_splat_levels_tc_dispatch(int n_levels, const void* const* scores, co
   RenderTcLevels L{};
   TcPlan first{};
   for (int i = 0; i < n_levels; ++i) {
-    const TcPlan pl = plan_tc(K, C[i], dtype == BLOBSPLAT_F32);
+    const TcPlan pl = plan_tc(K, C[i], split_of(dtype));
     if (!pl.ok) return 1;
     if (i == 0) first = pl;
     else if (pl.Kp != first.Kp || pl.c_tile != first.c_tile || pl.smem != first.smem) return 1;
