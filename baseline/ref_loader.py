@@ -35,11 +35,13 @@ def load(need_pipeline: bool = True):
     if REF_DIR not in sys.path:
         sys.path.insert(0, REF_DIR)
     ns = _ns or types.SimpleNamespace(utils=None, pipeline=None)
-    if need_pipeline and ns.pipeline is None:
+    if "diffusers" not in sys.modules:
+        # always, even when only the renderer is wanted: the fork must be imported BEFORE the matplotlib stub exists (its
+        # find_spec("matplotlib") probe rejects a spec-less module) or a later load(need_pipeline=True) would fail
         import transformers.utils as TU
         if not hasattr(TU, "FLAX_WEIGHTS_NAME"):
             TU.FLAX_WEIGHTS_NAME = "flax_model.msgpack"
-        import diffusers                                   # BEFORE the matplotlib stub (its find_spec probe)
+        import diffusers
         assert os.path.abspath(diffusers.__file__).startswith(REF_DIR), f"diffusers resolved to {diffusers.__file__}"
     if "matplotlib" not in sys.modules:
         try:

@@ -75,6 +75,9 @@
 #ifndef BS_SPLIT_ALIGN
 #define BS_SPLIT_ALIGN 8        // both blob ranges are whole groups of this many blobs when M allows
 #endif
+#ifndef BS_ALIGNED_SPLIT
+#define BS_ALIGNED_SPLIT 1      // split the blobs on an operand k-group boundary: one pair barrier per tile instead of three
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
@@ -247,6 +250,31 @@ __device__ __forceinline__ void store_pixel_pairs(float* oc, size_t P, const uin
   }
 }
 
+// G (8 or 4) blobs m-G+1 .. m of one pixel, front to back: branch-free, their MUFU/FMA chains interleave and only the
+// transmittance T is a serial dependence (one FFMA per blob).  d_k goes to the composed planes (when wr) and to the stash
+// as aligned float4s — m must be a multiple of 4 (plane m sits at stash column m + kTcKOff... the caller passes my = row + kTcKOff).
+template <typename OT, int G>
+__device__ __forceinline__ void composite_group(const BlobCoef* coef, int m, float xf, float yf, float& T, float* my, OT* comp_px,
+                                                size_t P, bool wr) {
+  float s[G], d[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) s[j] = BS_ABL_NO_COMPUTE ? 0.01f : blob_opacity_pd(coef[m - 1 - j], xf, yf);
+  OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    d[j] = s[j] * T;
+    T = fmaf(-s[j], T, T);
+  }
+#pragma unroll
+  for (int j = 0; j < G; j += 2) store_pair<OT>(cp - (ptrdiff_t)j * P, cp - (ptrdiff_t)(j + 1) * P, d[j], d[j + 1], wr);
+  if constexpr (G == 8) {
+    *reinterpret_cast<float4*>(my + m - 7) = make_float4(d[7], d[6], d[5], d[4]);
+    *reinterpret_cast<float4*>(my + m - 3) = make_float4(d[3], d[2], d[1], d[0]);
+  } else {
+    *reinterpret_cast<float4*>(my + m - 3) = make_float4(d[3], d[2], d[1], d[0]);
+  }
+}
+
 struct RenderTcParams {
   const float* xs; const float* ys; const float* covs; const float* sizes;
   const void* scores; long long sn, sk, sp;   // kFromScores: precomputed weights [N,K,P] with element strides
@@ -284,51 +312,129 @@ struct TcBarriers {
   float unit_inv[8];           // kSplit = 2: 1 / (power-of-two feature scale) of unit u in slot u & 7, applied by the drain.  8 slots:
                                // a slot is rewritten 8 units later, by which time the drain has long read it (its d_empty arrivals
                                // gate the MMAs of every unit in between)
-  float red[8];                // scratch of the staging threads' max reduction
+  float red[8];                // scratch of the staging threads' max reduction (ring mode)
+  float umax[8][4];            // kSplit = 2 without the ring: max|f| of unit u, one partial per drain warp, in slot u & 7
+  uint64_t s_full[2];          // ... unit u arrives on s_full[u & 1] (4 arrivals).  Two barriers: the drain warps run up to one unit
+                               // ahead of the staging that waits, and a single barrier's parity cannot tell phase u from u + 2
 };
 
 // Stage one unit's B operand: features [K, C] (c contiguous) of image n, channels c0 .. c0 + c_tile - 1, into the K-major
 // no-swizzle operand layout at b_dst (second copy = TF32 residuals at + b_bytes).  Called by `nthreads` threads.
 // kSplit = 2 additionally needs `sc` (TcBarriers: reduction scratch + the slot's inverse scale) and a named barrier shared by
 // exactly the calling threads.
-template <typename FT, typename OT, int kSplit>
+// max |f| over one unit's features (rows k < K, channels c0 .. c0 + c_tile - 1), this thread's share
+template <typename FT>
+__device__ __forceinline__ float unit_abs_max(const RenderTcParams& p, const FT* f, int c0, int tid, int nthreads) {
+  const int cw = min(p.c_tile, p.C - c0);
+  float mx = 0.0f;
+  if constexpr (sizeof(FT) == 4) {
+    if ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 3) == 0 && (cw & 3) == 0) {
+      const int q4 = cw >> 2, items = p.K * q4;
+      constexpr int kB = 8;                                   // loads in flight per thread
+      for (int i0 = tid; i0 < items; i0 += kB * nthreads) {
+        float4 v[kB];
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+          const int i = i0 + b * nthreads;
+          const int k = i / q4, c = (i - k * q4) << 2;
+          v[b] = i < items ? __ldg(reinterpret_cast<const float4*>(f + (size_t)k * p.C + c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < kB; ++b)
+          mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[b].x), fabsf(v[b].y)), fmaxf(fabsf(v[b].z), fabsf(v[b].w))));
+      }
+      return mx;
+    }
+  }
+  for (int i = tid; i < p.K * cw; i += nthreads) {
+    const int k = i / cw, c = i - k * cw;
+    mx = fmaxf(mx, fabsf((float)Cvt<FT>::to(__ldg(f + (size_t)k * p.C + c0 + c))));
+  }
+  return mx;
+}
+
+template <typename FT, typename OT, int kSplit, bool kEpiMax = false>
 __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c0, unsigned char* b_smem, size_t b_bytes,
-                                           int tid, int nthreads, TcBarriers* sc = nullptr, int slot = 0, int bar_id = 0) {
+                                           int tid, int nthreads, TcBarriers* sc = nullptr, int unit = 0, int bar_id = 0) {
   constexpr bool kTf32 = kSplit == 1;
   constexpr bool kH2 = kSplit == 2;
   using BT = typename std::conditional<kTf32, float, typename std::conditional<kH2, __half, OT>::type>::type;
-  float scale = 1.0f;
   if constexpr (kH2) {
-    // power-of-two scale of this unit's features: max|f| * scale in [0.5, 1), so fp16's absolute resolution (2^-24) is
-    // relative to the unit's own magnitude whatever the features' range
+    // Power-of-two scale of this unit's features: max|f| * scale in [0.5, 1), so fp16's absolute resolution (2^-24) is
+    // relative to the unit's own magnitude whatever the features' range.  The max comes from the drain warps, which
+    // computed it one unit ahead while they were waiting for accumulators (kEpiMax), or — with the B ring, where the
+    // staging warps run several units ahead — from a first pass over the features here.
     const FT* f = reinterpret_cast<const FT*>(p.feats) + (size_t)n * p.K * p.C;
-    const int cw = min(p.c_tile, p.C - c0);
     float mx = 0.0f;
-    if ((reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 3) == 0 && (cw & 3) == 0) {
-      const int q4 = cw >> 2;
-      for (int i = tid; i < p.K * q4; i += nthreads) {
-        const int k = i / q4, c = (i - k * q4) << 2;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(f + (size_t)k * p.C + c0 + c));
-        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-      }
+    if (kEpiMax) {
+      mbar_wait(&sc->s_full[unit & 1], (uint32_t)((unit >> 1) & 1));
+      mx = fmaxf(fmaxf(sc->umax[unit & 7][0], sc->umax[unit & 7][1]), fmaxf(sc->umax[unit & 7][2], sc->umax[unit & 7][3]));
     } else {
-      for (int i = tid; i < p.K * cw; i += nthreads) {
-        const int k = i / cw, c = i - k * cw;
-        mx = fmaxf(mx, fabsf((float)__ldg(f + (size_t)k * p.C + c0 + c)));
-      }
-    }
+      mx = unit_abs_max<FT>(p, f, c0, tid, nthreads);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((tid & 31) == 0) sc->red[tid >> 5] = mx;
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
-    mx = 0.0f;
-    for (int w = 0; w < (nthreads >> 5); ++w) mx = fmaxf(mx, sc->red[w]);
-    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");      // scratch may be rewritten by the next unit
+      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      if ((tid & 31) == 0) sc->red[tid >> 5] = mx;
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+      mx = 0.0f;
+      for (int w = 0; w < (nthreads >> 5); ++w) mx = fmaxf(mx, sc->red[w]);
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");      // scratch may be rewritten by the next unit
+    }
     int e = 0;
     if (mx > 0.0f && mx < 3.0e38f) (void)frexpf(mx, &e);                            // mx = m * 2^e, m in [0.5, 1)
     e = max(-100, min(100, e));
-    scale = exp2f((float)-e);
-    if (tid == 0) sc->unit_inv[slot] = exp2f((float)e);
+    const float scale = exp2f((float)-e);
+    if (tid == 0) sc->unit_inv[unit & 7] = exp2f((float)e);
+    // features [K, C] -> K-major operand rows, x = f * scale split into x1 = fp16(x), x2 = fp16(x - x1).  One thread moves
+    // blocks of 8 k-rows x 4 channels (8 128-bit loads, transposed in registers into 4 items per operand); two blocks per
+    // iteration keep 16 loads in flight per thread, so the 83 KB of a BlobNet unit cost two load round trips.
+    constexpr int kBlk = 2;
+    const int cq = p.c_tile >> 2;
+    const int blocks = (p.Kp >> 3) * cq;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(p.feats) & 15) == 0 && (p.C & 3) == 0;
+    for (int q0 = tid; q0 < blocks; q0 += kBlk * nthreads) {
+      float4 v[kBlk][8];
+#pragma unroll
+      for (int b = 0; b < kBlk; ++b) {
+        const int qi = q0 + b * nthreads;
+        const int kc = qi / cq, ch = c0 + ((qi - kc * cq) << 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = kc * 8 + j - kTcKOff;                          // operand row k' = k + kTcKOff
+          const bool ok = qi < blocks && k >= 0 && k < p.K && ch < p.C;
+          v[b][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok && vec_ok) {
+            v[b][j] = __ldg(reinterpret_cast<const float4*>(f + (size_t)k * p.C + ch));
+          } else if (ok) {
+            const FT* src = f + (size_t)k * p.C + ch;
+            v[b][j].x = (float)__ldg(src);
+            if (ch + 1 < p.C) v[b][j].y = (float)__ldg(src + 1);
+            if (ch + 2 < p.C) v[b][j].z = (float)__ldg(src + 2);
+            if (ch + 3 < p.C) v[b][j].w = (float)__ldg(src + 3);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < kBlk; ++b) {
+        const int qi = q0 + b * nthreads;
+        if (qi >= blocks) break;
+        const int kc = qi / cq, c = (qi - kc * cq) << 2;
+        unsigned char* dst = b_smem + ((size_t)kc * p.c_tile + c) * 16;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          __half h1[8], h2[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float raw = cc == 0 ? v[b][j].x : (cc == 1 ? v[b][j].y : (cc == 2 ? v[b][j].z : v[b][j].w));
+            const float x = raw * scale;                               // exact: a power of two
+            h1[j] = __float2half_rn(x);
+            h2[j] = __float2half_rn(x - __half2float(h1[j]));
+          }
+          *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h1);
+          *reinterpret_cast<uint4*>(dst + cc * 16 + b_bytes) = *reinterpret_cast<const uint4*>(h2);
+        }
+      }
+    }
+    return;
   }
   if constexpr (kSplit == 0 && BS_B_NMAJOR) {
     // 16-bit maps: B is an N-MAJOR operand (channels contiguous, as the features are stored) in the no-swizzle
@@ -405,16 +511,6 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
         for (int j = 0; j < 4; ++j) { hi[j] = rna_tf32(v[j][cc]); lo[j] = rna_tf32(v[j][cc] - hi[j]); }
         *reinterpret_cast<float4*>(dst + cc * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(dst + cc * 16 + b_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      } else if constexpr (kH2) {
-        __half h1[8], h2[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float x = v[j][cc] * scale;                    // exact: a power of two
-          h1[j] = __float2half_rn(x);
-          h2[j] = __float2half_rn(x - __half2float(h1[j]));
-        }
-        *reinterpret_cast<uint4*>(dst + cc * 16) = *reinterpret_cast<const uint4*>(h1);
-        *reinterpret_cast<uint4*>(dst + cc * 16 + b_bytes) = *reinterpret_cast<const uint4*>(h2);
       } else {
         OT h[8];
 #pragma unroll
@@ -458,8 +554,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   const size_t b_stride = kNumB * b_bytes;                                 // one ring slot
   const int srow = p0.Kp + 4;                                               // stash row stride (floats): conflict-free LDS/STS.128
   float* stash = reinterpret_cast<float*>(smem + nb * b_stride);         // [128 pixels][Kp + 4] composed weights of one tile
-  float* carry = stash + (size_t)srow * kTcTileM;                         // [128] front-range transmittance per pixel
-  BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + kTcTileM);
+  float* carry = stash + (size_t)srow * kTcTileM;                         // [2][128] front-range transmittance per pixel, by tile parity
+  BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + 2 * kTcTileM);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -472,6 +568,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       }
       mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
       mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
+      mbar_init(&bars->s_full[0], 4); mbar_init(&bars->s_full[1], 4);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -559,7 +656,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       }
       if constexpr (!kRing) {   // single B buffer: staged here, after the MMAs of the previous unit have read it
         if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
-        tc_stage_b<FT, OT, kSplit>(p, n, c0, b_smem, b_bytes, ctid, kTcComputeThreads, bars, unit_it & 7, 1);
+        tc_stage_b<FT, OT, kSplit, kH2>(p, n, c0, b_smem, b_bytes, ctid, kTcComputeThreads, bars, unit_it, 1);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
         mbar_arrive(&bars->b_full[0]);
       }
@@ -573,12 +670,18 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       // Two-level multiplicative suffix scan across blobs: each range is composited with a local
       // transmittance; the back range is then scaled by the front range's total transmittance.
       // The back range carries the extra rescale pass, so it gets the smaller share (7/16) of the blobs.
-      // front range = M - m_split blobs: both ranges are whole groups of 8 whenever M is (no serial tail blobs; the
-      // serial tail costs ~2.3x per blob), and the back range stays the smaller one because it also rescales
-      int m_split = 0;
+      // Aligned split (g_split >= 0): m_split is chosen so that the front range starts on an operand k-group boundary
+      // (m_split + 1 + kTcKOff a multiple of the MMA's k-step).  Each warp then converts exactly the stash columns it wrote
+      // itself, and the only hand-over left inside a quarter is the front range's transmittance: one named barrier per
+      // tile instead of three (the ncu source page had 21 % of the compute warps' time in those barriers).
+      int m_split = 0, g_split = -1;
       if (kHalves == 2) {
         m_split = ((p.M * BS_SPLIT_NUM) >> 4) & ~(BS_SPLIT_ALIGN - 1);
         if (BS_SPLIT_ALIGN == 8 && ((p.M - m_split) & 7) != 0 && (p.M & 7) == 0) m_split = (p.M * BS_SPLIT_NUM >> 4) & ~7;
+        if (!kFromScores && BS_ALIGNED_SPLIT) {
+          const int cand = ((((p.M * BS_SPLIT_NUM) >> 4) + 1 + kTcKOff + kKStep / 2) / kKStep) * kKStep - 1 - kTcKOff;
+          if (cand >= 4 && cand * 4 >= p.M && cand * 8 <= p.M * 5) { m_split = cand; g_split = (cand + 1 + kTcKOff) / kKStep; }
+        }
       }
       const int m_lo = half ? 0 : m_split, m_hi = half ? m_split : p.M;
       const int pair_bar = 2 + q;                   // named barrier of this quarter's two warps (64 threads)
@@ -615,32 +718,18 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           const bool wr_now = wr && half == 0;          // the front range's values are final in the first pass
           OT* const comp_px = comp + pix;                 // this pixel in plane 0; plane k is + k*P
           int m = m_hi;
-          // serial head until the remaining blobs of the range are whole, float4-aligned groups of 8
-          for (; m >= m_lo + 1 && (any_general || (m & 7) != 0 || m < m_lo + 8); --m) {
+          // serial head until the top of the range is float4-aligned in the stash (m a multiple of 4)
+          for (; m >= m_lo + 1 && (any_general || (m & 3) != 0 || m < m_lo + 4); --m) {
             const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
             const float d = s * T;
             T = fmaf(-s, T, T);
             my[m] = d;
             if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
           }
-          // branch-free, 8 blobs in flight: the MUFU/FMA chains of different blobs interleave; only the
-          // transmittance T is a serial dependence (one FFMA per blob).  Planes m-7..m are two aligned float4s.
-          for (; m >= m_lo + 8; m -= 8) {
-            float s[8], d[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s[j] = BS_ABL_NO_COMPUTE ? 0.01f : blob_opacity_pd(coef[m - 1 - j], xf, yf);
-            OT* const cp = comp_px + (size_t)m * P;      // plane k = m; the group's other planes are immediates
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              d[j] = s[j] * T;
-              T = fmaf(-s[j], T, T);
-            }
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) store_pair<OT>(cp - (ptrdiff_t)j * P, cp - (ptrdiff_t)(j + 1) * P, d[j], d[j + 1], wr_now);
-            *reinterpret_cast<float4*>(my + m - 7) = make_float4(d[7], d[6], d[5], d[4]);
-            *reinterpret_cast<float4*>(my + m - 3) = make_float4(d[3], d[2], d[1], d[0]);
-          }
-          for (; m >= m_lo + 1; --m) {               // (only when the range is shorter than 8 after the head)
+          // branch-free groups of 8 blobs (then at most one of 4): planes m-7..m are two aligned float4s of the stash
+          for (; m >= m_lo + 8; m -= 8) composite_group<OT, 8>(coef, m, xf, yf, T, my, comp_px, (size_t)P, wr_now);
+          if (m >= m_lo + 4) { composite_group<OT, 4>(coef, m, xf, yf, T, my, comp_px, (size_t)P, wr_now); m -= 4; }
+          for (; m >= m_lo + 1; --m) {               // (fewer than 4 blobs left)
             const float s = any_general ? blob_opacity(coef[m - 1], xf, yf) : blob_opacity_pd(coef[m - 1], xf, yf);
             const float d = s * T;
             T = fmaf(-s, T, T);
@@ -648,13 +737,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             if (wr_now) __stcs(comp_px + (size_t)m * P, Cvt<OT>::from(d));
           }
           if constexpr (kHalves == 2) {
-            if (half == 0) carry[px] = T;
+            float* const cr = carry + (tile_it & 1) * kTcTileM;     // double-buffered: the front warp may be a tile ahead
+            if (half == 0) cr[px] = T;
             asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
           }
           if (half == kHalves - 1) {
             float c = 1.0f;
             if constexpr (kHalves == 2) {
-              c = carry[px];
+              c = carry[(tile_it & 1) * kTcTileM + px];
               int k = m_hi;
               for (; k >= 1 && ((k & 3) != 0 || k < 4); --k) {       // unaligned top of the range
                 const float v = my[k] * c;
@@ -680,14 +770,20 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             if (wr) __stcs(comp_px, Cvt<OT>::from(bg));
           }
         }
-        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
+        if constexpr (kHalves == 2) {
+          if (g_split < 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash columns complete
+        }
+        // this warp's operand k-groups: its own range's (aligned split) or every kHalves-th one
+        const int g_lo = g_split < 0 ? half : (half ? 0 : g_split);
+        const int g_hi = g_split < 0 ? p.Kp / kKStep : (half ? g_split : p.Kp / kKStep);
+        const int g_inc = g_split < 0 ? kHalves : 1;
         if (ctid == 0 && tile_it == 0) TC_STAMP(3);    // first tile's weights in the stash
 
         if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
         tc_fence_after();
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
         if constexpr (kTf32) {
-          for (int g = half; g < p.Kp / 8; g += kHalves) {  // the warps of a quarter interleave the k-groups
+          for (int g = g_lo; g < g_hi; g += g_inc) {
             uint32_t hi[8], lo[8];
             const float4 wa = *reinterpret_cast<const float4*>(my - kTcKOff + g * 8);      // operand rows 8g .. 8g+7
             const float4 wb = *reinterpret_cast<const float4*>(my - kTcKOff + g * 8 + 4);
@@ -704,7 +800,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           }
         } else if constexpr (kH2) {
           // 2xFP16: w = w1 + w2 exactly to 2^-24; two k per 32-bit column, 8 columns = 16 consecutive k per operand
-          for (int g = half; g < p.Kp / 16; g += kHalves) {
+          for (int g = g_lo; g < g_hi; g += g_inc) {
             uint32_t p1[8], p2[8];
             const float* row = my - kTcKOff + g * 16;
             const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
@@ -723,7 +819,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
           }
         } else {
           // two k per 32-bit column (low half = even k): 8 columns = 16 consecutive k
-          for (int g = half; g < p.Kp / 16; g += kHalves) {
+          for (int g = g_lo; g < g_hi; g += g_inc) {
             uint32_t pk[8];
             const float* row = my - kTcKOff + g * 16;                                       // operand rows 16g .. 16g+15
             const float4 q0 = *reinterpret_cast<const float4*>(row), q1 = *reinterpret_cast<const float4*>(row + 4);
@@ -747,13 +843,35 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         tc_fence_before();
         mbar_arrive(&bars->a_full);
         if (ctid == 0 && tile_it == 0) TC_STAMP(4);    // first A in TMEM
-        if constexpr (kHalves == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+        if constexpr (kHalves == 2) {
+          if (g_split < 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+        }
       }
     } else if (warp < kTcComputeWarps + 4) {
       // ========================================= epilogue ==========================================
       const int q = warp - kTcComputeWarps;        // TMEM lane quarter
       OT* out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
       float inv = 1.0f;                             // kSplit = 2: read once the unit's first accumulator has landed
+      if constexpr (kH2 && !kRing) {
+        // max|f| of the NEXT unit's features (and of the first one), computed here while this warp would only wait for
+        // the unit's first accumulator: the compute warps' operand staging then converts in a single pass
+        const int et = (warp - kTcComputeWarps) * 32 + lane;
+        for (int which = (unit_it == 0 ? 0 : 1); which < 2; ++which) {
+          int n2 = n, c02 = c0, lv2 = kP == -1 ? level : 0;
+          if (which == 1) {
+            if (gs >= g_end) break;
+            if constexpr (kP == -1) { while (gs >= L.tile_start[lv2 + 1]) ++lv2; }
+            const RenderTcParams& pn = L.lv[lv2];
+            const int ic = (gs - (kP == -1 ? L.tile_start[lv2] : 0)) / pn.tiles_per_image;
+            n2 = ic / pn.c_chunks; c02 = (ic - n2 * pn.c_chunks) * pn.c_tile;
+          }
+          const RenderTcParams& pu = L.lv[lv2];
+          float mx = unit_abs_max<FT>(pu, reinterpret_cast<const FT*>(pu.feats) + (size_t)n2 * pu.K * pu.C, c02, et, 128);
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+          if (lane == 0) { bars->umax[(unit_it + which) & 7][q] = mx; mbar_arrive(&bars->s_full[(unit_it + which) & 1]); }
+        }
+      }
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
         // same lane -> pixel map as stages 1+2
         const int pix = (t_lo + t) * kTcTileM + q * 32 + (kFloatMaps ? ((lane & 15) << 1) + (lane >> 4) : lane);
@@ -875,7 +993,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
       const int buf = unit_it % nb, rnd = unit_it / nb;
       if (rnd > 0) mbar_wait(&bars->b_free[buf], (rnd - 1) & 1);
       tc_stage_b<FT, OT, kSplit>(p, n, c0, b_smem + (size_t)buf * b_stride, b_bytes, (int)threadIdx.x - (kTcMmaWarp + 1) * 32,
-                                 kTcStageWarps * 32, bars, unit_it & 7, 7);
+                                 kTcStageWarps * 32, bars, unit_it, 7);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> tensor-core reads
       mbar_arrive(&bars->b_full[buf]);
     }
@@ -923,7 +1041,7 @@ static inline TcPlan plan_tc(int K, int C, int split) {
   if (C < 1) { pl.why = "no channels"; return pl; }
   const int a_cols = tf32 ? 2 * pl.Kp : (split == 2 ? pl.Kp : pl.Kp / 2);
   const size_t per_c = (size_t)pl.Kp * (tf32 ? 8 : (split == 2 ? 4 : 2));   // B bytes per channel (hi+lo fp32 | x1+x2 fp16 | 16-bit)
-  const size_t fixed = (size_t)(pl.Kp + 4) * kTcTileM * 4 + kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
+  const size_t fixed = (size_t)(pl.Kp + 4) * kTcTileM * 4 + 2 * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) + sizeof(TcBarriers) + 512;
   int c_tile = std::min(kTcMaxCTile, round_up(C, 32));     // any C: the last chunk may be ragged (zero B columns, predicated drain)
   c_tile = std::min(c_tile, (512 - a_cols) / 32 * 32);
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);

@@ -166,9 +166,10 @@ def splat_features(
         kw = {k: v for k, v in kwargs.items() if k != "cuda_graph"}
         tensors = (xs, ys, covs, sizes, features, kw.get("viz_colors"))
         if graphs.capturable(*tensors) and (viz_score_fn is None or viz_score_fn is _IDENTITY_VIZ_SCORE_FN):
-            key = ("splat_features", graphs.tensor_key(tensors), graphs.tensor_key((score_size, viz_size)), interp_size, is_viz,
+            key = ("splat_features", graphs.tensor_key(tensors), score_size, viz_size, interp_size, is_viz,
                    ret_layout, viz_score_fn is None, return_d_score, only_vis, only_splatting_fg, only_splatting_bg,
-                   tuple(sorted((k, v) for k, v in kw.items() if not torch.is_tensor(v))))
+                   tuple(sorted((k, v) for k, v in kw.items() if not torch.is_tensor(v))) if len(kw) > 1 else
+                   tuple((k, v) for k, v in kw.items() if not torch.is_tensor(v)))
             return graphs.call(key, lambda: splat_features(xs, ys, covs, sizes, score_size, interp_size, features, viz_size,
                                                            is_viz, ret_layout, viz_score_fn, return_d_score, only_vis,
                                                            only_splatting_fg, only_splatting_bg, **kw), keepalive=tensors)

@@ -8,12 +8,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
     "cur": "",
+    "split8": "-DBS_SPLIT_NUM=8",
+    "abl_nostores": "-DBS_ABL_NO_EPI_STORE=1 -DBS_ABL_NO_COMP_STORE=1", "abl_nocompute": "-DBS_ABL_NO_COMPUTE=1",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 
 def build():
     for name, flags in VARIANTS.items():
         out = os.path.join(VDIR, name)
+        if os.path.exists(os.path.join(out, "libblobsplat.so")) and "--force" not in sys.argv:
+            continue
         os.makedirs(out, exist_ok=True)
         subprocess.run(["make", "-C", os.path.join(ROOT, "blobctrl_b200", "csrc"), "-j8", f"EXTRA={flags}",
                         f"OBJDIR={os.path.join(ROOT, 'build', 'variants', name)}", f"OUT={os.path.join(out, 'libblobsplat.so')}"],
