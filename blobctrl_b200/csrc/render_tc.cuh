@@ -75,6 +75,12 @@
 #ifndef BS_SPLIT_ALIGN
 #define BS_SPLIT_ALIGN 8        // both blob ranges are whole groups of this many blobs when M allows
 #endif
+#ifndef BS_D_PARTS
+#define BS_D_PARTS 1            // accumulate / drain the channel tile in 64-channel parts (else two halves)
+#endif
+#ifndef BS_A_BUFS
+#define BS_A_BUFS 2             // double-buffer the A operand in tensor memory when the columns allow
+#endif
 #ifndef BS_ALIGNED_SPLIT
 #define BS_ALIGNED_SPLIT 1      // split the blobs on an operand k-group boundary: one pair barrier per tile instead of three
 #endif
@@ -103,6 +109,7 @@ constexpr int kTcMaxCTile = 320;
 // pixel-major stash, so stage 1/2, the rescale pass and the TMEM conversion all use 128-bit shared-memory accesses.
 constexpr int kTcKOff = 3;
 constexpr int kTcMaxB = 4;                       // ring of B operand buffers (when they fit)
+constexpr int kTcMaxParts = 8;                   // accumulator parts per tile (ring of MMA -> drain hand-overs)
 constexpr int kTcStageWarps = 3;                 // staging warps: with the 13 others a CTA is 16 warps (registers are
                                                  // allocated for warp counts rounded up to 4 anyway)
 constexpr int kTcMaxBlobs = 127;                 // coefficient table: 127 * 32 B
@@ -290,6 +297,9 @@ struct RenderTcParams {
   int total_tiles;        // N * c_chunks * tiles_per_image, linear index ((n * c_chunks + chunk) * tiles_per_image + tile)
   int pair_ok;            // float maps: grid planes allow aligned 2-pixel stores (P even, base 8-byte aligned)
   int tmem_cols;          // tensor-memory columns to allocate: accumulator + A operands, rounded up to a power of two
+  int n_parts;            // the channel tile is accumulated and drained in n_parts parts of c_tile / n_parts channels: the MMAs of
+                          // part j of tile t + 1 start as soon as part j of tile t has been drained
+  int a_bufs;             // A operand buffers in tensor memory (2: stages 1+2 and the conversion run a tile ahead of the MMAs)
 };
 
 // First tile of CTA i's range under the equal-shares schedule.
@@ -307,7 +317,7 @@ struct RenderTcLevels {
 };
 
 struct TcBarriers {
-  uint64_t a_full, a_free, b_full[kTcMaxB], b_free[kTcMaxB], d_full[2], d_empty[2];
+  uint64_t a_full[2], a_free[2], b_full[kTcMaxB], b_free[kTcMaxB], d_full[kTcMaxParts], d_empty[kTcMaxParts];
   uint32_t tmem_base;
   float unit_inv[8];           // kSplit = 2: 1 / (power-of-two feature scale) of unit u in slot u & 7, applied by the drain.  8 slots:
                                // a slot is rewritten 8 units later, by which time the drain has long read it (its d_empty arrivals
@@ -547,7 +557,8 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   constexpr int kNumB = kFloatMaps ? 2 : 1;                        // hi + lo / x1 + x2
   constexpr int kACols = kTf32 ? 1 : 2;                            // k elements per 32-bit TMEM column
 
-  const int c_half = p0.c_tile >> 1;
+  const int n_parts = p0.n_parts;
+  const int c_half = p0.c_tile / n_parts;          // channels per accumulator part (historic name: there used to be two)
   const size_t b_bytes = (size_t)(p0.Kp / kElemsPer16B) * p0.c_tile * 16;   // one B copy
   unsigned char* b_smem = smem;                                            // [nb][kNumB][Kp/T][c_tile][16 B]
   const int nb = kRing ? p0.nb : 1;
@@ -562,12 +573,12 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
 
   if (warp == kTcMmaWarp) {
     if (lane == 0) {
-      mbar_init(&bars->a_full, kTcComputeThreads); mbar_init(&bars->a_free, 1);
+      mbar_init(&bars->a_full[0], kTcComputeThreads); mbar_init(&bars->a_free[0], 1);
+      mbar_init(&bars->a_full[1], kTcComputeThreads); mbar_init(&bars->a_free[1], 1);
       for (int i = 0; i < kTcMaxB; ++i) {   // B is staged by the staging warps when there is a ring, else by the compute warps
         mbar_init(&bars->b_full[i], kRing ? kTcStageWarps * 32 : kTcComputeThreads); mbar_init(&bars->b_free[i], 1);
       }
-      mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
-      mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
+      for (int i = 0; i < kTcMaxParts; ++i) { mbar_init(&bars->d_full[i], 1); mbar_init(&bars->d_empty[i], 128); }
       mbar_init(&bars->s_full[0], 4); mbar_init(&bars->s_full[1], 4);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -582,8 +593,10 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
   if (threadIdx.x == 0) TC_STAMP(1);
   pdl_launch_dependents();
   pdl_wait();                                      // set-up above overlapped the previous kernel's tail
-  const uint32_t tmem_a = tmem + (uint32_t)p0.c_tile;             // A hi; A lo follows at + Kp/kACols columns
-  const int a_cols = p0.Kp / kACols;
+  const int a_cols = p0.Kp / kACols;                               // columns of one A operand
+  const int a_bufs = p0.a_bufs;                                    // tile t uses buffer t % a_bufs
+  const uint32_t tmem_a0 = tmem + (uint32_t)p0.c_tile;             // buffer 0: A hi (x1); A lo (x2) follows at + a_cols columns
+  const uint32_t a_buf_cols = (uint32_t)((kFloatMaps ? 2 : 1) * a_cols);
 
   int unit_it = 0;      // units processed by this CTA so far
   int tile_it = 0;      // tiles processed by this CTA so far (barrier phases)
@@ -779,8 +792,10 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         const int g_inc = g_split < 0 ? kHalves : 1;
         if (ctid == 0 && tile_it == 0) TC_STAMP(3);    // first tile's weights in the stash
 
-        if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
+        const int abuf = a_bufs == 2 ? (tile_it & 1) : 0, ause = a_bufs == 2 ? (tile_it >> 1) : tile_it;   // buffer, its use count
+        if (ause > 0) mbar_wait(&bars->a_free[abuf], (ause - 1) & 1);   // the MMAs of the tile that last used this buffer have read it
         tc_fence_after();
+        const uint32_t tmem_a = tmem_a0 + (uint32_t)abuf * a_buf_cols;
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
         if constexpr (kTf32) {
           for (int g = g_lo; g < g_hi; g += g_inc) {
@@ -841,7 +856,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->a_full);
+        mbar_arrive(&bars->a_full[abuf]);
         if (ctid == 0 && tile_it == 0) TC_STAMP(4);    // first A in TMEM
         if constexpr (kHalves == 2) {
           if (g_split < 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
@@ -877,7 +892,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         const int pix = (t_lo + t) * kTcTileM + q * 32 + (kFloatMaps ? ((lane & 15) << 1) + (lane >> 4) : lane);
         const bool live = pix < P;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < n_parts; ++h) {
           mbar_wait(&bars->d_full[h], tile_it & 1);
           if (q == 0 && tile_it == 0) TC_STAMP(5 + h);   // first D half ready
           tc_fence_after();
@@ -959,9 +974,11 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
         mbar_wait(&bars->b_full[buf], rnd & 1);
         for (int t = 0; t < ntiles; ++t, ++tile_it) {
-          mbar_wait(&bars->a_full, tile_it & 1);
+          const int abuf = a_bufs == 2 ? (tile_it & 1) : 0, ause = a_bufs == 2 ? (tile_it >> 1) : tile_it;
+          mbar_wait(&bars->a_full[abuf], ause & 1);
           tc_fence_after();
-          for (int h = 0; h < 2; ++h) {
+          const uint32_t tmem_a = tmem_a0 + (uint32_t)abuf * a_buf_cols;
+          for (int h = 0; h < n_parts; ++h) {
             if (tile_it > 0) mbar_wait(&bars->d_empty[h], (tile_it - 1) & 1);
             tc_fence_after();
             const uint32_t d_addr = tmem + (uint32_t)(h * c_half);
@@ -981,7 +998,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
             }
             tc_commit(&bars->d_full[h]);
           }
-          tc_commit(&bars->a_free);
+          tc_commit(&bars->a_free[abuf]);
         }
         tc_commit(&bars->b_free[buf]);
       }
@@ -1001,7 +1018,11 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
 
   // the last commits arrive asynchronously: see them land before the CTA (and its smem barriers) goes away
   if (warp == kTcMmaWarp && lane == 0 && tile_it > 0) {
-    mbar_wait(&bars->a_free, (tile_it - 1) & 1);
+    {
+      const int last = tile_it - 1;
+      const int abuf = a_bufs == 2 ? (last & 1) : 0, ause = a_bufs == 2 ? (last >> 1) : last;
+      mbar_wait(&bars->a_free[abuf], ause & 1);
+    }
     mbar_wait(&bars->b_free[(unit_it - 1) % nb], ((unit_it - 1) / nb) & 1);
   }
   tc_fence_before();
@@ -1016,7 +1037,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
 // ---- host side ---------------------------------------------------------------------------------------
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-struct TcPlan { int Kp, c_tile, nb, tmem_cols; size_t smem, b_slot; bool ok; const char* why; };   // smem = fixed part + nb * b_slot
+struct TcPlan { int Kp, c_tile, nb, tmem_cols, n_parts, a_bufs; size_t smem, b_slot; bool ok; const char* why; };   // smem = fixed part + nb * b_slot
 
 // float32 maps: which split-precision form (header of this file).  BLOBSPLAT_F32_SPLIT=tf32 selects 3xTF32 (A/B knob).
 static inline int f32_split() {
@@ -1054,7 +1075,9 @@ static inline TcPlan plan_tc(int K, int C, int split) {
   pl.nb = (int)std::min<size_t>(BS_MAX_B, (kTcSmemBudget - fixed) / (per_c * c_tile));
   pl.b_slot = per_c * c_tile;
   pl.smem = fixed + (size_t)pl.nb * pl.b_slot;
-  pl.tmem_cols = tmem_cols_for(c_tile + a_cols);
+  pl.a_bufs = (BS_A_BUFS >= 2 && c_tile + 2 * a_cols <= 512) ? 2 : 1;
+  pl.tmem_cols = tmem_cols_for(c_tile + pl.a_bufs * a_cols);
+  pl.n_parts = (BS_D_PARTS && c_tile % 64 == 0 && c_tile / 64 >= 2 && c_tile / 64 <= kTcMaxParts) ? c_tile / 64 : 2;
   pl.ok = true;
   return pl;
 }
@@ -1063,7 +1086,7 @@ static inline TcPlan plan_tc(int K, int C, int split) {
 static int fill_tc_units(RenderTcParams& p, const TcPlan& pl, int N, int K, int H, int W, int C, int tile_px = kTcTileM) {
   p.N = N; p.M = K - 1; p.H = H; p.W = W; p.C = C; p.K = K; p.Kp = pl.Kp;
   p.c_tile = pl.c_tile; p.c_chunks = (C + pl.c_tile - 1) / pl.c_tile;
-  p.tmem_cols = pl.tmem_cols;
+  p.tmem_cols = pl.tmem_cols; p.n_parts = pl.n_parts; p.a_bufs = pl.a_bufs;
   const int P = H * W;
   p.tiles_per_image = (P + tile_px - 1) / tile_px;
   const long long total = (long long)N * p.c_chunks * p.tiles_per_image;

@@ -99,7 +99,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      mbar_init(&bars->a_full, kComputeThreads); mbar_init(&bars->a_free, 1);
+      mbar_init(&bars->a_full[0], kComputeThreads); mbar_init(&bars->a_free[0], 1);
       for (int i = 0; i < kTcMaxB; ++i) {
         mbar_init(&bars->b_full[i], kRing ? kTcStageWarps * 32 : kComputeThreads); mbar_init(&bars->b_free[i], 1);
       }
@@ -280,7 +280,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         }
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash rows complete
 
-        if (tile_it > 0) mbar_wait(&bars->a_free, (tile_it - 1) & 1);   // previous tile's MMAs have read A
+        if (tile_it > 0) mbar_wait(&bars->a_free[0], (tile_it - 1) & 1);   // previous tile's MMAs have read A
         tc_fence_after();
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
         for (int g = half; g < p.Kp / 16; g += 2) {          // the two warps of a quarter interleave the k-groups
@@ -298,7 +298,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bars->a_full);
+        mbar_arrive(&bars->a_full[0]);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
       }
     } else if (warp < kComputeWarps + 4) {
@@ -344,7 +344,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
         mbar_wait(&bars->b_full[buf], rnd & 1);
         for (int t = 0; t < ntiles; ++t, ++tile_it) {
-          mbar_wait(&bars->a_full, tile_it & 1);
+          mbar_wait(&bars->a_full[0], tile_it & 1);
           tc_fence_after();
           for (int j = 0; j < nsub; ++j, ++sub_it) {
             const int slot = sub_it & 1;
@@ -363,7 +363,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
             }
             tc_commit(&bars->d_full[slot]);
           }
-          tc_commit(&bars->a_free);
+          tc_commit(&bars->a_free[0]);
         }
         tc_commit(&bars->b_free[buf]);
       }
@@ -379,7 +379,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   }
 
   if (warp == kMmaWarp && lane == 0 && tile_it > 0) {
-    mbar_wait(&bars->a_free, (tile_it - 1) & 1);
+    mbar_wait(&bars->a_free[0], (tile_it - 1) & 1);
     mbar_wait(&bars->b_free[(unit_it - 1) % nb], ((unit_it - 1) / nb) & 1);
   }
   tc_fence_before();

@@ -7,9 +7,9 @@ import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "cur": "",
-    "split8": "-DBS_SPLIT_NUM=8",
-    "abl_nostores": "-DBS_ABL_NO_EPI_STORE=1 -DBS_ABL_NO_COMP_STORE=1", "abl_nocompute": "-DBS_ABL_NO_COMPUTE=1",
+    "r2_all": "",
+    "r2_noparts": "-DBS_D_PARTS=0", "r2_abuf1": "-DBS_A_BUFS=1", "r2_noalign": "-DBS_ALIGNED_SPLIT=0",
+    "r2_base": "-DBS_D_PARTS=0 -DBS_A_BUFS=1 -DBS_ALIGNED_SPLIT=0",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 
