@@ -78,19 +78,22 @@ __device__ __forceinline__ void drain16(OT* oc, size_t P, const uint32_t* e, con
   }
 }
 
+// kP = -1: several stage-3 problems of one pyramid (RenderTcLevels) in ONE launch over the concatenated tile sequence —
+// every work unit reads its own level's shape, pointers and strides; Kp, c_tile, cw and the B ring are common.
 template <typename OT, int kP, bool kFromScores, bool kRing>
 __global__ void __launch_bounds__((13 + (kRing ? kTcStageWarps : 0)) * 32, 1)
 render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
-  const RenderTcParams& p = L.lv[0];
+  const RenderTcParams& p0 = L.lv[0];
+  constexpr bool kLevels = kP == -1;
+  static_assert(!kLevels || kFromScores, "a multi-level launch is stage 3 from score maps");
   constexpr int kComputeWarps = 8, kComputeThreads = 256, kMmaWarp = 12;
   extern __shared__ __align__(1024) unsigned char smem[];
 
-  const int P = kP > 0 ? kP : p.H * p.W;
-  const int cw = p.cw, nsub = p.c_tile / cw;                              // drain sub-steps of cw channels
-  const size_t b_bytes = (size_t)(p.Kp / 8) * p.c_tile * 16;             // one B buffer (N-major, see tc_stage_b)
-  const int nb = kRing ? p.nb : 1;
+  const int cw = p0.cw, nsub = p0.c_tile / cw;                            // drain sub-steps of cw channels
+  const size_t b_bytes = (size_t)(p0.Kp / 8) * p0.c_tile * 16;           // one B buffer (N-major, see tc_stage_b)
+  const int nb = kRing ? p0.nb : 1;
   unsigned char* b_smem = smem;
-  const int srow = p.Kp + 4;
+  const int srow = p0.Kp + 4;
   float* stash = reinterpret_cast<float*>(smem + (size_t)nb * b_bytes);  // [2 parities][128 lanes][Kp + 4]
   float* carry = stash + (size_t)2 * kTcTileM * srow;                    // [2][128] front-range transmittances
   BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + 2 * kTcTileM);
@@ -118,20 +121,28 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   pdl_launch_dependents();
   pdl_wait();                                            // set-up above overlapped the previous kernel's tail
   const uint32_t tmem_a = tmem + (uint32_t)(4 * cw);     // A even; A odd follows at + a_cols
-  const int a_cols = p.Kp / 2;                           // two k per 32-bit column
+  const int a_cols = p0.Kp / 2;                          // two k per 32-bit column
 
   int unit_it = 0, tile_it = 0;
   int sub_it = 0;                                        // drain sub-steps so far (slot = sub_it & 1)
 
-  const bool whole_runs = p.whole_runs;
-  const int g_end = whole_runs ? p.total_tiles : tc_range_begin(p.total_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
-  for (int gs = whole_runs ? (int)blockIdx.x * p.tiles_per_image : tc_range_begin(p.total_tiles, (int)blockIdx.x, (int)gridDim.x);
+  const int seq_tiles = kLevels ? L.tile_start[L.n_levels] : p0.total_tiles;
+  const bool whole_runs = !kLevels && p0.whole_runs;
+  const int g_end = whole_runs ? seq_tiles : tc_range_begin(seq_tiles, (int)blockIdx.x + 1, (int)gridDim.x);
+  int level = 0;
+  for (int gs = whole_runs ? (int)blockIdx.x * p0.tiles_per_image : tc_range_begin(seq_tiles, (int)blockIdx.x, (int)gridDim.x);
        gs < g_end; ++unit_it) {
-    const int img_chunk = gs / p.tiles_per_image;
+    if constexpr (kLevels) {
+      while (gs >= L.tile_start[level + 1]) ++level;
+    }
+    const RenderTcParams& p = L.lv[kLevels ? level : 0];
+    const int P = kP > 0 ? kP : p.H * p.W;
+    const int g = gs - (kLevels ? L.tile_start[level] : 0);         // tile index within the level
+    const int img_chunk = g / p.tiles_per_image;
     const int n = img_chunk / p.c_chunks;
     const int chunk = img_chunk - n * p.c_chunks;
     const int c0 = chunk * p.c_tile;
-    const int t_lo = gs - img_chunk * p.tiles_per_image;
+    const int t_lo = g - img_chunk * p.tiles_per_image;
     const int ntiles = min(p.tiles_per_image - t_lo, g_end - gs);
     gs += ntiles;
     if (whole_runs) gs += ((int)gridDim.x - 1) * p.tiles_per_image;
@@ -421,9 +432,10 @@ static inline Tc2Plan plan_tc2(int K, int C) {
 
 // Can this 16-bit problem run on the two-pixels-per-lane kernel?
 static inline bool render_tc2_usable(int dtype, int H, int W, const void* composed, const void* grid, const void* scores,
-                                     long long sn, long long sk, long long sp) {
+                                     long long sn, long long sk, long long sp, bool any_size = false) {
   if (!BS_PX2 || !BS_B_NMAJOR || (dtype != BLOBSPLAT_BF16 && dtype != BLOBSPLAT_F16)) return false;
-  if ((W & 1) != 0 || (long long)H * W < kTc2TilePx) return false;      // small images: the 128-pixel tile wastes less
+  if ((W & 1) != 0) return false;
+  if (!any_size && (long long)H * W < kTc2TilePx) return false;        // small images: the 128-pixel tile wastes less (single launches)
   if (((reinterpret_cast<uintptr_t>(composed) | reinterpret_cast<uintptr_t>(grid)) & 3) != 0) return false;
   if (scores && (sp != 1 || (sk & 1) != 0 || (sn & 1) != 0 || (reinterpret_cast<uintptr_t>(scores) & 3) != 0)) return false;
   return true;
@@ -458,6 +470,28 @@ static int launch_tc2(const RenderTcParams& p, cudaStream_t st) {
     case 256: return ring ? launch_tc2_pr<OT, 256, kFromScores, true>(p, st) : launch_tc2_pr<OT, 256, kFromScores, false>(p, st);
   }
   return ring ? launch_tc2_pr<OT, 0, kFromScores, true>(p, st) : launch_tc2_pr<OT, 0, kFromScores, false>(p, st);
+}
+
+// Several stage-3 problems of one pyramid in one launch (kP = -1): L.lv[*] filled by fill_tc_units with the 256-pixel tile.
+template <typename OT, bool kRing>
+static int launch_tc2_levels(RenderTcLevels& L, cudaStream_t st) {
+  static thread_local int configured_dev = -1, sm_count = 0;
+  int dev = 0;
+  BS_CUDA(cudaGetDevice(&dev));
+  if (configured_dev != dev) {
+    BS_CUDA(cudaFuncSetAttribute(render_tc2_kernel<OT, -1, true, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    configured_dev = dev;
+  }
+  long long total = 0;
+  for (int i = 0; i < L.n_levels; ++i) { L.tile_start[i] = (int)total; total += L.lv[i].total_tiles; }
+  if (total > 0x7fffffffll) BS_UNSUPPORTED("too many tiles for one launch");
+  L.tile_start[L.n_levels] = (int)total;
+  if (total == 0) return 0;
+  const int grid = (int)std::min<long long>(sm_count, total);
+  BS_CUDA(launch_pdl(render_tc2_kernel<OT, -1, true, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
+                     (size_t)L.lv[0].smem_bytes, st, L));
+  return 0;
 }
 
 // Fill the plan-dependent fields and launch.  p: pointers (and score strides) already set.

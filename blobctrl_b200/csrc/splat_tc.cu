@@ -68,6 +68,39 @@ int feature_splat_levels_tc_dispatch(int n_levels, const void* const* scores, co
                                      const int64_t* sp, const void* const* feats, void* const* outs, int N, int K,
                                      const int* C, const int* H, const int* W, int dtype, cudaStream_t st) {
   if (n_levels < 2 || n_levels > kTcMaxLevels || dtype == BLOBSPLAT_F64) return 1;
+  // 16-bit maps: the two-pixels-per-lane kernel when every level qualifies (even widths, aligned pixel-contiguous maps) and
+  // the levels share Kp / channel tile / drain sub-step
+  if (dtype == BLOBSPLAT_BF16 || dtype == BLOBSPLAT_F16) {
+    bool ok2 = true;
+    Tc2Plan first2{};
+    RenderTcLevels L2{};
+    for (int i = 0; i < n_levels && ok2; ++i) {
+      ok2 = render_tc2_usable(dtype, H[i], W[i], nullptr, outs[i], scores[i], sn[i], sk[i], sp[i], /*any_size=*/true);
+      if (!ok2) break;
+      const Tc2Plan pl2 = plan_tc2(K, C[i]);
+      if (!pl2.ok) { ok2 = false; break; }
+      if (i == 0) first2 = pl2;
+      else if (pl2.Kp != first2.Kp || pl2.c_tile != first2.c_tile || pl2.cw != first2.cw || pl2.nb != first2.nb) { ok2 = false; break; }
+      RenderTcParams& p = L2.lv[i];
+      p.scores = scores[i]; p.sn = sn[i]; p.sk = sk[i]; p.sp = sp[i]; p.feats = feats[i]; p.grid = outs[i];
+      TcPlan base{};
+      base.Kp = pl2.Kp; base.c_tile = pl2.c_tile; base.nb = pl2.nb; base.smem = pl2.smem; base.b_slot = pl2.b_slot; base.ok = true;
+      if (int rc = fill_tc_units(p, base, N, K, H[i], W[i], C[i], kTc2TilePx)) return rc;
+      p.cw = pl2.cw;
+    }
+    if (ok2) {
+      L2.n_levels = n_levels;
+      // a pyramid launch has many short units per CTA: always use the B ring when more than one buffer fits
+      const bool ring = first2.nb > 1;
+      for (int i = 0; i < n_levels; ++i) {
+        L2.lv[i].nb = ring ? first2.nb : 1;
+        L2.lv[i].smem_bytes = (int)(first2.smem - (size_t)(first2.nb - L2.lv[i].nb) * first2.b_slot);
+      }
+      if (dtype == BLOBSPLAT_BF16)
+        return ring ? launch_tc2_levels<__nv_bfloat16, true>(L2, st) : launch_tc2_levels<__nv_bfloat16, false>(L2, st);
+      return ring ? launch_tc2_levels<__half, true>(L2, st) : launch_tc2_levels<__half, false>(L2, st);
+    }
+  }
   RenderTcLevels L{};
   TcPlan first{};
   for (int i = 0; i < n_levels; ++i) {
