@@ -15,7 +15,7 @@ import torch
 F32, F64, BF16, F16 = 0, 1, 2, 3
 SELECT_ALL, SELECT_FG, SELECT_BG = 0, 1, 2
 COMPOSITE_AUTO, COMPOSITE_LANE_PIXEL, COMPOSITE_WARP_SCAN = 0, 1, 2
-ENGINE_AUTO, ENGINE_FMA, ENGINE_TENSOR = 0, 1, 2
+ENGINE_AUTO, ENGINE_FMA, ENGINE_TENSOR, ENGINE_TMA = 0, 1, 2, 3
 ABI_VERSION = 2
 
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}

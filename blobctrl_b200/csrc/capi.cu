@@ -32,6 +32,10 @@ int feature_splat_fma_dispatch(const void*, int64_t, int64_t, int64_t, const voi
                                int, cudaStream_t);
 int feature_splat_tc_dispatch(const void*, int64_t, int64_t, int64_t, const void*, void*, int, int, int, int, int, int,
                               cudaStream_t);
+bool splat_tma_usable(int, const void* const*, const int64_t*, const int64_t*, const int64_t*, const void* const*, void* const*,
+                      int, int, const int*, const int*, const int*, int);
+int splat_tma_dispatch(int, const void* const*, const int64_t*, const int64_t*, const void* const*, void* const*, int, int,
+                       const int*, const int*, const int*, int, cudaStream_t);
 int feature_splat_levels_tc_dispatch(int, const void* const*, const int64_t*, const int64_t*, const int64_t*,
                                      const void* const*, void* const*, int, int, const int*, const int*, const int*, int,
                                      cudaStream_t);
@@ -49,6 +53,9 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
 constexpr int kMaxBlobs = 1 << 20;
+#ifndef BS_TMA_LEVELS_AUTO
+#define BS_TMA_LEVELS_AUTO 1     // AUTO runs 16-bit pyramids on the TMA engine (splat_tma.cu)
+#endif
 #ifndef BS_FUSE_LEVELS_AUTO
 #define BS_FUSE_LEVELS_AUTO 0
 #endif
@@ -176,7 +183,7 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
   BS_CHECK_ARG(N >= 0 && K >= 1 && C >= 1 && H >= 1 && W >= 1, "bad shape N=%d K=%d C=%d H=%d W=%d", N, K, C, H, W);
   BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535, "shape too large");
   BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
-  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TENSOR, "bad engine %d", engine);
+  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TMA, "bad engine %d", engine);
   BS_CHECK_ARG(stride_k >= 0 && stride_p >= 1 && stride_n >= 0, "bad strides");
   if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(scores && features && out, "NULL pointer");
@@ -184,6 +191,16 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
   if (g.status) return g.status;
   // Stage 3 is a dense contraction [P x K] x [K x C]: on tensor cores (tcgen05, weights staged into TMEM) when
   // K and C make it one, on CUDA-core FMA tiles otherwise (tiny K: the K = 1 pipeline splat, C = 3 previews).
+  if (engine == BLOBSPLAT_ENGINE_TMA) {
+    if (!splat_tma_usable(1, &scores, &stride_n, &stride_k, &stride_p, &features, &out, N, K, &C, &H, &W, dtype))
+      BS_UNSUPPORTED("TMA feature splat: needs 16-bit, 16-byte aligned, pixel-contiguous maps with H*W and C multiples of 8");
+    return splat_tma_dispatch(1, &scores, &stride_n, &stride_k, &features, &out, N, K, &C, &H, &W, dtype, (cudaStream_t)stream);
+  }
+  // AUTO, 16-bit maps, a large output (>= 2^28 elements): the TMA engine's store stream wins (cfg5c's stage 3 alone,
+  // 1024 images: 0.65 ms vs 0.77 ms); smaller launches stay on the thread-staged tensor engine (64 images: 37 vs 43 us)
+  if (engine == BLOBSPLAT_ENGINE_AUTO && BS_TMA_LEVELS_AUTO && C >= 64 && K >= 12 && (long long)N * C * H * W >= (1ll << 28) &&
+      splat_tma_usable(1, &scores, &stride_n, &stride_k, &stride_p, &features, &out, N, K, &C, &H, &W, dtype))
+    return splat_tma_dispatch(1, &scores, &stride_n, &stride_k, &features, &out, N, K, &C, &H, &W, dtype, (cudaStream_t)stream);
   const char* why = nullptr;
   const bool tc_ok = dtype != BLOBSPLAT_F64 && render_tc_supported(K, C, H, W, dtype, dtype, &why);
   if (engine == BLOBSPLAT_ENGINE_TENSOR && !tc_ok) BS_UNSUPPORTED("tensor-core feature splat: %s", why ? why : "float64");
@@ -206,12 +223,25 @@ int blobsplat_feature_splat_levels(int n_levels, const void* const* scores, cons
   BS_CHECK_ARG(n_levels >= 0 && n_levels <= 16, "bad level count %d", n_levels);
   if (n_levels == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(scores && stride_n && stride_k && stride_p && features && outs && C && H && W, "NULL level array");
-  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TENSOR, "bad engine %d", engine);
+  BS_CHECK_ARG(engine >= BLOBSPLAT_ENGINE_AUTO && engine <= BLOBSPLAT_ENGINE_TMA, "bad engine %d", engine);
   BS_CHECK_ARG(valid_dtype(dtype), "bad dtype %d", dtype);
   // One launch for the whole pyramid when every level is a dense contraction with the same operand tiling
   // (BlobNet's 640/1280-channel levels); otherwise level by level.  BS_FUSE_LEVELS_AUTO: whether AUTO fuses too —
   // measured on cfg3 (profiles/render_tc_r1.md) the per-level launches with their compile-time plane strides win
   // until operand staging overlaps across units, so AUTO stays level by level and TENSOR asks for the single launch.
+  // 16-bit pyramids: the TMA engine takes all levels in one launch (AUTO for a real contraction, or on request)
+  if (N > 0 && n_levels <= 4 && (engine == BLOBSPLAT_ENGINE_TMA || (engine == BLOBSPLAT_ENGINE_AUTO && BS_TMA_LEVELS_AUTO && n_levels >= 2 && K >= 12))) {
+    bool ok = true;
+    for (int i = 0; i < n_levels && ok; ++i) ok = scores[i] && features[i] && outs[i] && (C[i] >= 64 || engine == BLOBSPLAT_ENGINE_TMA) && H[i] >= 1 && W[i] >= 1;
+    ok = ok && splat_tma_usable(n_levels, scores, stride_n, stride_k, stride_p, features, outs, N, K, C, H, W, dtype);
+    if (ok) {
+      DeviceGuard g(device);
+      if (g.status) return g.status;
+      return splat_tma_dispatch(n_levels, scores, stride_n, stride_k, features, outs, N, K, C, H, W, dtype, (cudaStream_t)stream);
+    }
+    if (engine == BLOBSPLAT_ENGINE_TMA)
+      BS_UNSUPPORTED("TMA feature splat: needs 16-bit, 16-byte aligned, pixel-contiguous maps with H*W and C multiples of 8");
+  }
   bool fuse = N > 0 && n_levels >= 2 && n_levels <= 4 && dtype != BLOBSPLAT_F64 &&
               (engine == BLOBSPLAT_ENGINE_TENSOR || (BS_FUSE_LEVELS_AUTO && engine == BLOBSPLAT_ENGINE_AUTO && K >= 12));
   for (int i = 0; i < n_levels && fuse; ++i) {

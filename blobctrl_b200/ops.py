@@ -14,7 +14,7 @@ from . import _capi as C
 
 _SELECT = {"all": C.SELECT_ALL, "fg": C.SELECT_FG, "bg": C.SELECT_BG}
 _MODE = {"auto": C.COMPOSITE_AUTO, "lane_pixel": C.COMPOSITE_LANE_PIXEL, "warp_scan": C.COMPOSITE_WARP_SCAN}
-_ENGINE = {"auto": C.ENGINE_AUTO, "fma": C.ENGINE_FMA, "tensor": C.ENGINE_TENSOR}
+_ENGINE = {"auto": C.ENGINE_AUTO, "fma": C.ENGINE_FMA, "tensor": C.ENGINE_TENSOR, "tma": C.ENGINE_TMA}
 
 _HALF = (torch.bfloat16, torch.float16)
 

@@ -72,7 +72,8 @@ typedef enum {
 typedef enum {
   BLOBSPLAT_ENGINE_AUTO = 0,
   BLOBSPLAT_ENGINE_FMA = 1,    /* CUDA-core FP32/FP64 FMA tiles */
-  BLOBSPLAT_ENGINE_TENSOR = 2  /* tcgen05 MMA (bf16/f16: kind::f16; f32: 3xTF32 split) */
+  BLOBSPLAT_ENGINE_TENSOR = 2, /* tcgen05 MMA, weights staged into tensor memory by threads (bf16/f16: kind::f16; f32: split precision) */
+  BLOBSPLAT_ENGINE_TMA = 3     /* 16-bit maps only: operands by TMA loads, tcgen05 MMA from shared memory, output by TMA stores */
 } blobsplat_engine;
 
 typedef struct {

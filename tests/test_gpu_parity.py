@@ -649,16 +649,24 @@ def test_feature_splat_levels_vs_oracle(n, k, levels, dtype, rel):
         fts.append(torch.randn(n, k, c, generator=g).to(DEV).to(dtype))
     outs = ops.feature_splat_levels(scs, fts)
     assert len(outs) == len(levels)
+    fused = None
     if k >= 12 and all(c % 32 == 0 and c >= 64 for _, _, c in levels):
-        fused = ops.feature_splat_levels(scs, fts, engine="tensor")      # the single-launch path
-        for a, b in zip(fused, outs):
-            assert torch.equal(a, b), "single-launch pyramid differs from the per-level launches"
-    for (h, w, c), sc, ft, out in zip(levels, scs, fts, outs):
+        fused = ops.feature_splat_levels(scs, fts, engine="tensor")      # the thread-staged single-launch path
+    # 16-bit pyramids take the TMA engine under AUTO (splat_tma.cu): same products, another fp32 summation order, so the
+    # engines may differ in the last 16-bit place — each is held to the oracle; float32 paths stay bit-identical
+    exact = dtype == torch.float32
+    for i, ((h, w, c), sc, ft, out) in enumerate(zip(levels, scs, fts, outs)):
         assert out.shape == (n, c, h, w) and out.dtype == dtype and out.is_contiguous()
         want = blob_oracle.splat_features_from_scores(_np(sc).astype(np.float64), _np(ft).astype(np.float64), None,
                                                       channels_last=False)
         close_scaled(_np(out), want, rel, f"level {h}x{w} C={c}")
-        assert torch.equal(out, ops.feature_splat(sc, ft)), f"level {h}x{w}: differs from the single-level call"
+        single = ops.feature_splat(sc, ft)
+        close_scaled(_np(single), want, rel, f"single-level call, level {h}x{w} C={c}")
+        if fused is not None:
+            close_scaled(_np(fused[i]), want, rel, f"tensor engine, level {h}x{w} C={c}")
+            assert torch.equal(fused[i], single), "single-launch pyramid (tensor engine) differs from the per-level launches"
+        if exact:
+            assert torch.equal(out, single), f"level {h}x{w}: differs from the single-level call"
     assert ops.feature_splat_levels([], []) == []
 
 
@@ -720,10 +728,12 @@ def test_render_multiscale_one_call_equals_the_call_sequence(dtype):
     d0, g0 = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats[0], s, s, out_dtype=dtype)
     pyr = ops.halving_pyramid(d0, s >> 3)
     assert torch.equal(comps[0], d0) and torch.equal(grids[0], g0) and grids[1] is None
+    lv = [l for l in range(1, 4) if feats[l] is not None]
+    seq = ops.feature_splat_levels([pyr[s >> l] for l in lv], [feats[l] for l in lv])
     for l in range(1, 4):
         assert torch.equal(comps[l], pyr[s >> l])
-        if feats[l] is not None:
-            assert torch.equal(grids[l], ops.feature_splat(pyr[s >> l], feats[l]))
+    for l, want in zip(lv, seq):
+        assert torch.equal(grids[l], want)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -949,3 +959,53 @@ def test_cfg4_edit_loop_latent_parity_toy_width(dtype):
     assert a["calls"]["canvas_updates"] == 12
     assert a["latent_rel_to_absmax"] <= (1e-4 if dtype == torch.float32 else 1e-2), a
     assert b["latent_rel_to_absmax"] <= (1e-3 if dtype == torch.float32 else 1e-2), b
+
+
+@pytest.mark.parametrize("dtype,rel", [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+@pytest.mark.parametrize("n,k,levels", [
+    (2, 33, [(32, 32, 640), (16, 16, 1280), (8, 8, 1280)]),                    # cfg3's lower levels: one launch
+    (3, 17, [(64, 64, 320)]),                                                  # 2.5 channel groups: clipped third group
+    (1, 1, [(64, 64, 1024)]),                                                  # the pipeline's K = 1 splat: exact
+    (2, 65, [(64, 64, 320), (32, 32, 640)]),                                   # Kp = 80: shallower rings
+    (2, 5, [(24, 24, 72), (12, 12, 136), (4, 4, 8)]),                          # ragged pixel and channel tails, 16-pixel image
+    (1, 128, [(48, 40, 200)]),                                                 # K = 128 (the thread-staged engine stops at 127 blobs + bg)
+    (5, 33, [(8, 8, 64), (4, 2, 1280)]),                                       # 8-pixel image: one 16-column MMA
+    (2, 40, [(20, 18, 328), (10, 12, 96), (64, 64, 320), (2, 4, 64)])])        # four levels of unrelated shapes
+def test_tma_engine_vs_oracle(n, k, levels, dtype, rel):
+    """splat_tma.cu (engine='tma'): operands by TMA, tcgen05 from shared memory, 128-byte line stores — every level against
+    the float64 contraction of the same 16-bit inputs (utils.py:57-77), as one launch and level by level."""
+    from blobctrl_b200 import ops
+    g = torch.Generator().manual_seed(n * 17 + k)
+    scs, fts = [], []
+    for (h, w, c) in levels:
+        sc = torch.rand(n, k, h, w, generator=g)
+        scs.append((sc / sc.sum(1, keepdim=True)).to(DEV).to(dtype))
+        fts.append(torch.randn(n, k, c, generator=g).to(DEV).to(dtype))
+    outs = ops.feature_splat_levels(scs, fts, engine="tma")
+    for (h, w, c), sc, ft, out in zip(levels, scs, fts, outs):
+        assert out.shape == (n, c, h, w) and out.dtype == dtype and out.is_contiguous()
+        want = torch.einsum("nkhw,nkc->nchw", sc.double(), ft.double()).cpu().numpy()
+        close_scaled(_np(out), want, rel, f"level {h}x{w} C={c}")
+        assert torch.equal(out, ops.feature_splat(sc, ft, engine="tma")), "one launch != level by level on the same engine"
+        if k == 1:
+            assert torch.equal(out, torch.einsum("nkhw,nkc->nchw", sc.float(), ft.float()).to(dtype)), "a single product is exact"
+
+
+def test_tma_engine_views_and_envelope():
+    """Strided score views are consumed in place; shapes outside the TMA envelope raise BlobSplatUnsupported on request and
+    fall back to the other engines under AUTO."""
+    from blobctrl_b200 import ops, _capi as C
+    g = torch.Generator().manual_seed(5)
+    big = torch.rand(2, 20, 40, 32, generator=g).to(DEV).to(torch.bfloat16)
+    view = big[:, 2:19, :32, :]                          # plane stride 1280 > 1024 pixels, image stride 20 planes
+    ft = torch.randn(2, 17, 256, generator=g).to(DEV).to(torch.bfloat16)
+    out = ops.feature_splat(view, ft, engine="tma")
+    want = torch.einsum("nkhw,nkc->nchw", view.double(), ft.double()).cpu().numpy()
+    close_scaled(_np(out), want, 1e-2, "strided view")
+    for sc, f in ((torch.rand(2, 17, 8, 8, device=DEV), torch.randn(2, 17, 64, device=DEV)),                       # float32
+                  (torch.rand(2, 17, 5, 5, device=DEV).bfloat16(), torch.randn(2, 17, 64, device=DEV).bfloat16()),  # 25 pixels
+                  (torch.rand(2, 17, 8, 8, device=DEV).bfloat16(), torch.randn(2, 17, 60, device=DEV).bfloat16())):  # C % 8 != 0
+        with pytest.raises(C.BlobSplatUnsupported):
+            ops.feature_splat(sc, f, engine="tma")
+        ref = torch.einsum("nkhw,nkc->nchw", sc.double(), f.double()).cpu().numpy()
+        close_scaled(_np(ops.feature_splat(sc, f)), ref, 1e-5 if sc.dtype == torch.float32 else 1e-2, "AUTO fallback")
