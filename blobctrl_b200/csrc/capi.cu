@@ -1,5 +1,6 @@
 // extern "C" surface of libblobsplat.so — argument validation, device guard, dispatch.
 // Declarations and the reference interfaces each entry replaces: include/blobsplat.h.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -36,6 +37,8 @@ bool splat_tma_usable(int, const void* const*, const int64_t*, const int64_t*, c
                       int, int, const int*, const int*, const int*, int);
 int splat_tma_dispatch(int, const void* const*, const int64_t*, const int64_t*, const void* const*, void* const*, int, int,
                        const int*, const int*, const int*, int, cudaStream_t);
+int render_tc_pyramid_dispatch(const float*, const float*, const float*, const float*, const void*, int, int, int, int, void*,
+                               void*, void* const*, int, int, cudaStream_t);
 int feature_splat_levels_tc_dispatch(int, const void* const*, const int64_t*, const int64_t*, const int64_t*,
                                      const void* const*, void* const*, int, int, const int*, const int*, const int*, int,
                                      cudaStream_t);
@@ -341,6 +344,9 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
                             (cudaStream_t)stream);
 }
 
+#ifndef BS_FUSED_PYRAMID
+#define BS_FUSED_PYRAMID 1      // multi-scale renders of 64 x 64 16-bit maps: the pyramid comes out of the render launch
+#endif
 int blobsplat_render_multiscale(const float* xs, const float* ys, const float* covs, const float* sizes, int N, int M,
                                 int S, int n_levels, const void* const* features, const int* C, void* const* composed,
                                 void* const* grids, int dtype, int device, void* stream) {
@@ -353,11 +359,30 @@ int blobsplat_render_multiscale(const float* xs, const float* ys, const float* c
   BS_CHECK_ARG(features[0] && grids[0] && composed[0], "level 0 needs features, a grid and a composed-map buffer");
   for (int l = 1; l < n_levels; ++l) BS_CHECK_ARG(composed[l] != nullptr, "level %d composed-map buffer is NULL", l);
   // level 0: stages 1+2+3 fused; levels 1..: exact 2x2 means of the composed maps, then stage 3 per level
-  int rc = blobsplat_render(xs, ys, covs, sizes, features[0], dtype, N, M, S, S, C[0], composed[0], grids[0], dtype, device,
-                            stream);
-  if (rc != BLOBSPLAT_OK || n_levels == 1) return rc;
-  rc = blobsplat_pyramid(composed[0], composed + 1, n_levels - 1, N * (M + 1), S, dtype, device, stream);
-  if (rc != BLOBSPLAT_OK) return rc;
+  int rc = 1;
+  static const bool fused_pyr = [] { const char* e = std::getenv("BLOBSPLAT_FUSED_PYRAMID"); return !(e && e[0] == '0'); }();   // A/B knob
+  if (n_levels > 1 && BS_FUSED_PYRAMID && fused_pyr && dtype != BLOBSPLAT_F32 && S == 64 && (M > 0 ? (xs && ys && covs && sizes) : true)) {
+    // BlobNet's latent size in 16 bits: the pyramid leaves the render launch itself (render_tc2.cuh, kPyr)
+    const char* why = nullptr;
+    if (render_tc_supported(M + 1, C[0], S, S, dtype, dtype, &why)) {
+      DeviceGuard g(device);
+      if (g.status) return g.status;
+      const int fused_levels = std::min(2, n_levels - 1);   // level 3 spans two tiles of the render: one more pyramid launch
+      rc = render_tc_pyramid_dispatch(xs, ys, covs, sizes, features[0], N, M, S, C[0], composed[0], grids[0], composed + 1,
+                                      fused_levels, dtype, (cudaStream_t)stream);
+      if (rc == 0 && n_levels - 1 > fused_levels)
+        rc = blobsplat_pyramid(composed[fused_levels], composed + 1 + fused_levels, n_levels - 1 - fused_levels, N * (M + 1),
+                               S >> fused_levels, dtype, device, stream);
+      if (rc < 0) return rc;
+    }
+  }
+  if (rc == 1) {
+    rc = blobsplat_render(xs, ys, covs, sizes, features[0], dtype, N, M, S, S, C[0], composed[0], grids[0], dtype, device, stream);
+    if (rc != BLOBSPLAT_OK || n_levels == 1) return rc;
+    rc = blobsplat_pyramid(composed[0], composed + 1, n_levels - 1, N * (M + 1), S, dtype, device, stream);
+    if (rc != BLOBSPLAT_OK) return rc;
+  }
+  if (n_levels == 1) return BLOBSPLAT_OK;
   const void* sc[4]; const void* ft[4]; void* out[4];
   int64_t sn[4], sk[4], sp[4];
   int Cs[4], Hs[4], Ws[4], n = 0;

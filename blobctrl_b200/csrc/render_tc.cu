@@ -16,6 +16,34 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
   return 1;
 }
 
+// The fused two-pixel render with the first one or two halvings of the composed maps in the same launch: 64 x 64 maps in
+// 16 bits, levels [N,K,32,32] and [N,K,16,16].  Returns 1 (nothing launched) when the shape is outside that envelope —
+// the caller runs render + pyramid kernel.
+int render_tc_pyramid_dispatch(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,
+                               int N, int M, int S, int C, void* composed, void* grid, void* const* pyr, int pyr_levels,
+                               int dtype, cudaStream_t st) {
+  if (S != 64 || pyr_levels < 1 || pyr_levels > 2 || !composed) return 1;
+  if (!render_tc2_usable(dtype, S, S, composed, grid, nullptr, 0, 0, 1)) return 1;
+  for (int l = 0; l < pyr_levels; ++l)
+    if (!pyr[l] || (reinterpret_cast<uintptr_t>(pyr[l]) & 15) != 0) return 1;      // bulk stores: 16-byte aligned rows
+  const Tc2Plan pl2 = plan_tc2(M + 1, C, /*pyr=*/true);
+  if (!pl2.ok) return 1;
+  RenderTcParams p{};
+  p.xs = xs; p.ys = ys; p.covs = covs; p.sizes = sizes; p.feats = features; p.composed = composed; p.grid = grid;
+  for (int l = 0; l < pyr_levels; ++l) p.pyr[l] = pyr[l];
+  p.pyr_levels = pyr_levels;
+  if (const char* e = std::getenv("BLOBSPLAT_PYR_DBG")) p.pyr_dbg = std::atoi(e);   // measurement only
+  // the pyramid warp takes the place of the B ring's staging warps: large batches, where the ring pays, keep the
+  // separate pyramid kernel (a few per cent of such a render)
+  TcPlan base{};
+  base.Kp = pl2.Kp; base.c_tile = pl2.c_tile; base.nb = pl2.nb; base.smem = pl2.smem; base.b_slot = pl2.b_slot; base.ok = true;
+  if (int rc = fill_tc_units(p, base, N, M + 1, S, S, C, kTc2TilePx)) return rc;
+  if (p.nb > 1) return 1;
+  p.cw = pl2.cw;
+  if (dtype == BLOBSPLAT_BF16) return launch_tc2<__nv_bfloat16, false>(p, st);
+  return launch_tc2<__half, false>(p, st);
+}
+
 int render_tc_dispatch(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,
                        int feat_dtype, int N, int M, int H, int W, int C, void* composed, void* grid, int out_dtype,
                        cudaStream_t st) {

@@ -66,6 +66,21 @@ __device__ __forceinline__ void store_px2(OT* p, float a, float b, bool pred) {
   if (pred) __stcs(reinterpret_cast<unsigned int*>(p), w);
 }
 
+// two adjacent pixels of one plane, and (fused pyramid) their horizontal half-sum as the level-1 resize sees them: rounded to
+// the map dtype first, 0.5 * a + 0.5 * b like pyramid_kernel (resize.cu)
+template <typename OT, bool kPyr>
+__device__ __forceinline__ void store_px2_h(OT* p, float a, float b, bool pred, float* hs, bool hs_pred) {
+  const uint32_t w = pack2<OT>(a, b);
+  if (pred) __stcs(reinterpret_cast<unsigned int*>(p), w);
+  if constexpr (kPyr) {
+    float ra, rb;
+    unpack2<OT>(w, ra, rb);
+    if (hs_pred) *hs = 0.5f * ra + 0.5f * rb;
+  }
+}
+template <typename OT>
+__device__ __forceinline__ float round_to(float v) { return Cvt<OT>::to(Cvt<OT>::from(v)); }
+
 // 16 channel planes of this lane's two pixels: e[i] / o[i] = fp32 accumulators of the even / odd pixel
 template <typename OT>
 __device__ __forceinline__ void drain16(OT* oc, size_t P, const uint32_t* e, const uint32_t* o, bool live, int left) {
@@ -80,9 +95,19 @@ __device__ __forceinline__ void drain16(OT* oc, size_t P, const uint32_t* e, con
 
 // kP = -1: several stage-3 problems of one pyramid (RenderTcLevels) in ONE launch over the concatenated tile sequence —
 // every work unit reads its own level's shape, pointers and strides; Kp, c_tile, cw and the B ring are common.
-template <typename OT, int kP, bool kFromScores, bool kRing>
-__global__ void __launch_bounds__((13 + (kRing ? kTcStageWarps : 0)) * 32, 1)
+// kPyr (fused render of 64 x 64 maps only): the halving pyramid of the composed maps (pyramid_resize, utils.py:280-294) leaves
+// the same launch.  Every final pair of composed values also goes, as its rounded horizontal half-sum, into a staging
+// array hs[slot][k][tile row] (hand-over by mbarriers hs_full / hs_free); three extra warps (the places of the B ring's
+// staging warps; one warp alone needs longer than a tile: shuffle / convert chains at one warp's issue rate) turn the tile's four image
+// rows into two level-1 rows and one level-2 row — exact 2x2 means, rounded between levels like the reference's repeated
+// interpolate.  Level 3 needs two tiles (eight image rows), which equal tile ranges split between CTAs: a cross-CTA
+// hand-over (arrival counter + __threadfence) was measured at +18 us .. +60 us on cfg3's level 64 — MEMBAR.GPU in an SM
+// whose store queue is saturated waits for the whole queue — so level 3 is one more (tiny) pyramid launch on level 2.
+template <typename OT, int kP, bool kFromScores, bool kRing, bool kPyr = false>
+__global__ void __launch_bounds__((13 + (kRing ? kTcStageWarps : 0) + (kPyr ? 3 : 0)) * 32, 1)
 render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
+  static_assert(!kPyr || (kP == 4096 && !kFromScores && !kRing), "the fused pyramid is specialised for 64 x 64 renders without the B ring");
+  constexpr int kPyrWarp = 13, kPyrWarps = 3;               // kPyr: warps 13-15 turn staged half-sums into pyramid rows (planes k = w, w + 3, ..)
   const RenderTcParams& p0 = L.lv[0];
   constexpr bool kLevels = kP == -1;
   static_assert(!kLevels || kFromScores, "a multi-level launch is stage 3 from score maps");
@@ -98,6 +123,8 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   float* carry = stash + (size_t)2 * kTcTileM * srow;                    // [2][128] front-range transmittances
   BlobCoef* coef = reinterpret_cast<BlobCoef*>(carry + 2 * kTcTileM);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
+  uint64_t* const hs_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(TcBarriers) + 15) & ~(size_t)15));   // kPyr: full[2], free[2]
+  float* const hs = reinterpret_cast<float*>(hs_bar + 4);                                                                // kPyr: [2][K][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kMmaWarp) {
@@ -108,6 +135,9 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
       }
       mbar_init(&bars->d_full[0], 1); mbar_init(&bars->d_full[1], 1);
       mbar_init(&bars->d_empty[0], 128); mbar_init(&bars->d_empty[1], 128);
+      if constexpr (kPyr) {
+        mbar_init(&hs_bar[0], kComputeWarps); mbar_init(&hs_bar[1], kComputeWarps); mbar_init(&hs_bar[2], kPyrWarps); mbar_init(&hs_bar[3], kPyrWarps);
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -124,6 +154,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   const int a_cols = p0.Kp / 2;                          // two k per 32-bit column
 
   int unit_it = 0, tile_it = 0;
+  int pyr_it = 0;                                        // kPyr: tiles that produced pyramid rows so far (staging slot = pyr_it & 1)
   int sub_it = 0;                                        // drain sub-steps so far (slot = sub_it & 1)
 
   const int seq_tiles = kLevels ? L.tile_start[L.n_levels] : p0.total_tiles;
@@ -221,6 +252,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
           const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE;
           const bool wr_now = wr && half == 0;
           OT* const comp_px = comp + pix0;
+          const bool do_pyr = kPyr && comp != nullptr && p.pyr_levels > 0;          // CTA-uniform
+          float* const hs_row = hs + (size_t)(pyr_it & 1) * p.K * kTcTileM + row;    // + k * 128: plane k of this tile row
+          const bool hs_wr = do_pyr && !(p.pyr_dbg & 4);
+          const bool hs_now = hs_wr && half == 0;
+          if constexpr (kPyr) {
+            if (do_pyr && pyr_it >= 2) mbar_wait(&hs_bar[2 + (pyr_it & 1)], (uint32_t)(((pyr_it >> 1) - 1) & 1));   // the pyramid warp has read this slot
+          }
           int m = m_hi;
           // serial head until the remaining blobs of the range are whole, float4-aligned groups of 4
           for (; m >= m_lo + 1 && (any_general || (m & 3) != 0 || m < m_lo + 4); --m) {
@@ -230,7 +268,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
             const float da = sa * Ta, db = sb * Tb;
             Ta = fmaf(-sa, Ta, Ta); Tb = fmaf(-sb, Tb, Tb);
             my_e[m] = da; my_o[m] = db;
-            store_px2<OT>(comp_px + (size_t)m * P, da, db, wr_now);
+            store_px2_h<OT, kPyr>(comp_px + (size_t)m * P, da, db, wr_now, hs_row + m * kTcTileM, hs_now);
           }
           // branch-free: 4 blobs x 2 pixels in flight
           for (; m >= m_lo + 4; m -= 4) {
@@ -244,7 +282,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
             }
             OT* const cp = comp_px + (size_t)m * P;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) store_px2<OT>(cp - (ptrdiff_t)j * P, da[j], db[j], wr_now);
+            for (int j = 0; j < 4; ++j) store_px2_h<OT, kPyr>(cp - (ptrdiff_t)j * P, da[j], db[j], wr_now, hs_row + (m - j) * kTcTileM, hs_now);
             *reinterpret_cast<float4*>(my_e + m - 3) = make_float4(da[3], da[2], da[1], da[0]);
             *reinterpret_cast<float4*>(my_o + m - 3) = make_float4(db[3], db[2], db[1], db[0]);
           }
@@ -255,7 +293,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
             const float da = sa * Ta, db = sb * Tb;
             Ta = fmaf(-sa, Ta, Ta); Tb = fmaf(-sb, Tb, Tb);
             my_e[m] = da; my_o[m] = db;
-            store_px2<OT>(comp_px + (size_t)m * P, da, db, wr_now);
+            store_px2_h<OT, kPyr>(comp_px + (size_t)m * P, da, db, wr_now, hs_row + m * kTcTileM, hs_now);
           }
           if (half == 0) { carry[row] = Ta; carry[kTcTileM + row] = Tb; }
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -265,7 +303,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
             for (; k >= 1 && ((k & 3) != 0 || k < 4); --k) {
               const float va = my_e[k] * ca, vb = my_o[k] * cb;
               my_e[k] = va; my_o[k] = vb;
-              store_px2<OT>(comp_px + (size_t)k * P, va, vb, wr);
+              store_px2_h<OT, kPyr>(comp_px + (size_t)k * P, va, vb, wr, hs_row + k * kTcTileM, hs_wr);
             }
             for (; k >= 4; k -= 4) {
               float4 a4 = *reinterpret_cast<const float4*>(my_e + k - 3), b4 = *reinterpret_cast<const float4*>(my_o + k - 3);
@@ -274,19 +312,19 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
               *reinterpret_cast<float4*>(my_e + k - 3) = a4;
               *reinterpret_cast<float4*>(my_o + k - 3) = b4;
               OT* const cp = comp_px + (size_t)k * P;
-              store_px2<OT>(cp, a4.w, b4.w, wr);
-              store_px2<OT>(cp - (ptrdiff_t)P, a4.z, b4.z, wr);
-              store_px2<OT>(cp - (ptrdiff_t)2 * P, a4.y, b4.y, wr);
-              store_px2<OT>(cp - (ptrdiff_t)3 * P, a4.x, b4.x, wr);
+              store_px2_h<OT, kPyr>(cp, a4.w, b4.w, wr, hs_row + k * kTcTileM, hs_wr);
+              store_px2_h<OT, kPyr>(cp - (ptrdiff_t)P, a4.z, b4.z, wr, hs_row + (k - 1) * kTcTileM, hs_wr);
+              store_px2_h<OT, kPyr>(cp - (ptrdiff_t)2 * P, a4.y, b4.y, wr, hs_row + (k - 2) * kTcTileM, hs_wr);
+              store_px2_h<OT, kPyr>(cp - (ptrdiff_t)3 * P, a4.x, b4.x, wr, hs_row + (k - 3) * kTcTileM, hs_wr);
             }
             for (; k >= 1; --k) {
               const float va = my_e[k] * ca, vb = my_o[k] * cb;
               my_e[k] = va; my_o[k] = vb;
-              store_px2<OT>(comp_px + (size_t)k * P, va, vb, wr);
+              store_px2_h<OT, kPyr>(comp_px + (size_t)k * P, va, vb, wr, hs_row + k * kTcTileM, hs_wr);
             }
             const float bga = Ta * ca, bgb = Tb * cb;          // background: alpha 1 * total transmittance
             my_e[0] = bga; my_o[0] = bgb;
-            store_px2<OT>(comp_px, bga, bgb, wr);
+            store_px2_h<OT, kPyr>(comp_px, bga, bgb, wr, hs_row, hs_wr);
           }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash rows complete
@@ -311,6 +349,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         tc_fence_before();
         mbar_arrive(&bars->a_full[0]);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+        if constexpr (kPyr) {
+          if (comp != nullptr && p.pyr_levels > 0) {           // this warp's half-sums of the tile are staged
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hs_bar[pyr_it & 1]);
+            ++pyr_it;
+          }
+        }
       }
     } else if (warp < kComputeWarps + 4) {
       // ============================ drain: (even, odd) pixel pairs, 32-bit stores ============================
@@ -379,6 +424,48 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         tc_commit(&bars->b_free[buf]);
       }
       __syncwarp();
+    } else if (kPyr && warp >= kPyrWarp) {
+      // ============================ fused pyramid: staged half-sums -> level 1 / 2 / 3 rows ============================
+      if constexpr (kPyr) {
+        if (p.composed != nullptr && chunk == 0 && p.pyr_levels > 0) {
+          for (int t = 0; t < ntiles; ++t, ++pyr_it) {
+            mbar_wait(&hs_bar[pyr_it & 1], (uint32_t)((pyr_it >> 1) & 1));
+            const float* const H = hs + (size_t)(pyr_it & 1) * p.K * kTcTileM;
+            const int tt = t_lo + t;                           // tile of the image: rows 4 tt .. 4 tt + 3
+            // four planes per step: one warp carries the whole tile, so the load -> mean -> round -> shuffle chains of
+            // independent planes have to overlap
+            OT* const l1 = reinterpret_cast<OT*>(p.pyr[0]) + (size_t)n * p.K * 1024 + (2 * tt) * 32 + lane;
+            OT* const l2 = p.pyr_levels >= 2 ? reinterpret_cast<OT*>(p.pyr[1]) + (size_t)n * p.K * 256 + tt * 16 + (lane >> 1) : nullptr;
+            constexpr int kU = 4;
+            for (int k0 = (warp - kPyrWarp) * kU; k0 < ((p.pyr_dbg & 1) ? 0 : p.K); k0 += kPyrWarps * kU) {
+              float v0[kU], v1[kU];
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const float* hk = H + min(k0 + u, p.K - 1) * kTcTileM;
+                v0[u] = round_to<OT>(0.5f * hk[lane] + 0.5f * hk[32 + lane]);        // level 1, row 2 tt
+                v1[u] = round_to<OT>(0.5f * hk[64 + lane] + 0.5f * hk[96 + lane]);   // level 1, row 2 tt + 1
+              }
+#pragma unroll
+              for (int u = 0; u < kU; ++u) {
+                const int k = k0 + u;
+                const bool ok = k < p.K && !(p.pyr_dbg & 2);
+                const float n0 = __shfl_down_sync(0xffffffffu, v0[u], 1), n1 = __shfl_down_sync(0xffffffffu, v1[u], 1);
+                store_px2<OT>(l1 + (size_t)k * 1024, v0[u], n0, ok && (lane & 1) == 0);
+                store_px2<OT>(l1 + (size_t)k * 1024 + 32, v1[u], n1, ok && (lane & 1) == 0);
+                if (l2 != nullptr) {
+                  const float g0 = 0.5f * v0[u] + 0.5f * __shfl_xor_sync(0xffffffffu, v0[u], 1);
+                  const float g1 = 0.5f * v1[u] + 0.5f * __shfl_xor_sync(0xffffffffu, v1[u], 1);
+                  const float w2 = round_to<OT>(0.5f * g0 + 0.5f * g1);                       // level 2, row tt, x = lane >> 1
+                  const float w2n = __shfl_down_sync(0xffffffffu, w2, 2);
+                  store_px2<OT>(l2 + (size_t)k * 256, w2, w2n, ok && (lane & 3) == 0);
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hs_bar[2 + (pyr_it & 1)]);   // the staging slot may be rewritten
+          }
+        }
+      }
     } else if constexpr (kRing) {
       const int buf = unit_it % nb, rnd = unit_it / nb;
       if (rnd > 0) mbar_wait(&bars->b_free[buf], (rnd - 1) & 1);
@@ -403,13 +490,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
 // ---- host side ------------------------------------------------------------------------------------------------
 struct Tc2Plan { int Kp, c_tile, cw, nb; size_t smem, b_slot; bool ok; };
 
-static inline Tc2Plan plan_tc2(int K, int C) {
+static inline Tc2Plan plan_tc2(int K, int C, bool pyr = false) {
   Tc2Plan pl{};
   pl.ok = false;
   if (K - 1 > kTcMaxBlobs || C < 1) return pl;
   pl.Kp = round_up(K + kTcKOff, 16);
   const size_t fixed = (size_t)2 * (pl.Kp + 4) * kTcTileM * 4 + 2 * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) +
-                       sizeof(TcBarriers) + 512;
+                       sizeof(TcBarriers) + 512 + (pyr ? (size_t)2 * K * kTcTileM * 4 + 64 : 0);   // + fused pyramid: hand-over barriers, hs[2][K][128]
   const size_t per_c = (size_t)pl.Kp * 2;
   if (fixed + per_c * 32 > kTcSmemBudget) return pl;
   int c_tile = std::min(kTcMaxCTile, round_up(C, 32));
@@ -441,13 +528,13 @@ static inline bool render_tc2_usable(int dtype, int H, int W, const void* compos
   return true;
 }
 
-template <typename OT, int kP, bool kFromScores, bool kRing>
+template <typename OT, int kP, bool kFromScores, bool kRing, bool kPyr = false>
 static int launch_tc2_pr(const RenderTcParams& p, cudaStream_t st) {
   static thread_local int configured_dev = -1, sm_count = 0;
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(render_tc2_kernel<OT, kP, kFromScores, kRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(render_tc2_kernel<OT, kP, kFromScores, kRing, kPyr>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured_dev = dev;
   }
@@ -456,14 +543,17 @@ static int launch_tc2_pr(const RenderTcParams& p, cudaStream_t st) {
   L.lv[0] = p;
   L.n_levels = 1;
   L.tile_start[1] = p.total_tiles;
-  BS_CUDA(launch_pdl(render_tc2_kernel<OT, kP, kFromScores, kRing>, dim3(grid), dim3((13 + (kRing ? kTcStageWarps : 0)) * 32),
-                     (size_t)p.smem_bytes, st, L));
+  BS_CUDA(launch_pdl(render_tc2_kernel<OT, kP, kFromScores, kRing, kPyr>, dim3(grid),
+                     dim3((13 + (kRing ? kTcStageWarps : 0) + (kPyr ? 3 : 0)) * 32), (size_t)p.smem_bytes, st, L));
   return 0;
 }
 
 template <typename OT, bool kFromScores>
 static int launch_tc2(const RenderTcParams& p, cudaStream_t st) {
   const bool ring = p.nb > 1;
+  if constexpr (!kFromScores) {
+    if (p.pyr_levels > 0) return launch_tc2_pr<OT, 4096, false, false, true>(p, st);   // 64 x 64 render + pyramid (caller checked nb == 1)
+  }
   switch (p.H * p.W) {
     case 4096: return ring ? launch_tc2_pr<OT, 4096, kFromScores, true>(p, st) : launch_tc2_pr<OT, 4096, kFromScores, false>(p, st);
     case 1024: return ring ? launch_tc2_pr<OT, 1024, kFromScores, true>(p, st) : launch_tc2_pr<OT, 1024, kFromScores, false>(p, st);

@@ -1009,3 +1009,36 @@ def test_tma_engine_views_and_envelope():
             ops.feature_splat(sc, f, engine="tma")
         ref = torch.einsum("nkhw,nkc->nchw", sc.double(), f.double()).cpu().numpy()
         close_scaled(_np(ops.feature_splat(sc, f)), ref, 1e-5 if sc.dtype == torch.float32 else 1e-2, "AUTO fallback")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("n,m,c,levels", [(5, 32, 320, 4), (3, 5, 64, 4), (2, 0, 32, 3), (70, 12, 96, 4), (4, 64, 352, 2),
+                                          (3, 100, 640, 4)])
+def test_fused_pyramid_equals_the_pyramid_kernel(n, m, c, levels, dtype):
+    """64 x 64 multi-scale renders in 16 bits: the halving pyramid (utils.py:280-294) leaves the render launch itself
+    (render_tc2.cuh kPyr: levels 1-2 per tile from staged half-sums, level 3 by the second tile of a pair).  Bit-identical to
+    blobsplat_render + blobsplat_pyramid, on repeated calls (the arrival counters reset themselves) and under a CUDA graph."""
+    from blobctrl_b200 import ops
+    syn = blob_oracle.synthetic_blobs(n, m, seed=n + m, c=1)
+    b = _blob(syn)
+    g = torch.Generator().manual_seed(11)
+    feats = [torch.randn(n, m + 1, c, generator=g).to(DEV).to(dtype)] + [None] * (levels - 1)
+    d0, g0 = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats[0], 64, 64, out_dtype=dtype)
+    pyr = ops.halving_pyramid(d0, 64 >> (levels - 1))
+    for rep in range(3):
+        comps, grids = ops.render_multiscale(b["xs"], b["ys"], b["covs"], b["sizes"], 64, feats, dtype)
+        assert torch.equal(comps[0], d0) and torch.equal(grids[0], g0)
+        for l in range(1, levels):
+            assert torch.equal(comps[l], pyr[64 >> l]), f"call {rep}: level {64 >> l} differs from the pyramid kernel"
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=st):
+            comps, grids = ops.render_multiscale(b["xs"], b["ys"], b["covs"], b["sizes"], 64, feats, dtype)
+        for _ in range(2):
+            for t in comps:
+                t.zero_()
+            gr.replay()
+    torch.cuda.synchronize()
+    for l in range(1, levels):
+        assert torch.equal(comps[l], pyr[64 >> l]), f"graph replay: level {64 >> l}"
