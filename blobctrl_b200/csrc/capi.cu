@@ -344,6 +344,9 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
                             (cudaStream_t)stream);
 }
 
+#ifndef BS_FUSED_PYRAMID_LEVELS
+#define BS_FUSED_PYRAMID_LEVELS 3
+#endif
 #ifndef BS_FUSED_PYRAMID
 #define BS_FUSED_PYRAMID 1      // multi-scale renders of 64 x 64 16-bit maps: the pyramid comes out of the render launch
 #endif
@@ -367,7 +370,7 @@ int blobsplat_render_multiscale(const float* xs, const float* ys, const float* c
     if (render_tc_supported(M + 1, C[0], S, S, dtype, dtype, &why)) {
       DeviceGuard g(device);
       if (g.status) return g.status;
-      const int fused_levels = std::min(2, n_levels - 1);   // level 3 spans two tiles of the render: one more pyramid launch
+      const int fused_levels = std::min(BS_FUSED_PYRAMID_LEVELS, n_levels - 1);
       rc = render_tc_pyramid_dispatch(xs, ys, covs, sizes, features[0], N, M, S, C[0], composed[0], grids[0], composed + 1,
                                       fused_levels, dtype, (cudaStream_t)stream);
       if (rc == 0 && n_levels - 1 > fused_levels)

@@ -16,13 +16,13 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
   return 1;
 }
 
-// The fused two-pixel render with the first one or two halvings of the composed maps in the same launch: 64 x 64 maps in
-// 16 bits, levels [N,K,32,32] and [N,K,16,16].  Returns 1 (nothing launched) when the shape is outside that envelope —
+// The fused two-pixel render with up to three halvings of the composed maps in the same launch: 64 x 64 maps in 16 bits,
+// levels [N,K,32,32], [N,K,16,16] and [N,K,8,8].  Returns 1 (nothing launched) when the shape is outside that envelope —
 // the caller runs render + pyramid kernel.
 int render_tc_pyramid_dispatch(const float* xs, const float* ys, const float* covs, const float* sizes, const void* features,
                                int N, int M, int S, int C, void* composed, void* grid, void* const* pyr, int pyr_levels,
                                int dtype, cudaStream_t st) {
-  if (S != 64 || pyr_levels < 1 || pyr_levels > 2 || !composed) return 1;
+  if (S != 64 || pyr_levels < 1 || pyr_levels > 3 || !composed) return 1;
   if (!render_tc2_usable(dtype, S, S, composed, grid, nullptr, 0, 0, 1)) return 1;
   for (int l = 0; l < pyr_levels; ++l)
     if (!pyr[l] || (reinterpret_cast<uintptr_t>(pyr[l]) & 15) != 0) return 1;      // bulk stores: 16-byte aligned rows

@@ -301,8 +301,8 @@ struct RenderTcParams {
                           // part j of tile t + 1 start as soon as part j of tile t has been drained
   int a_bufs;             // A operand buffers in tensor memory (2: stages 1+2 and the conversion run a tile ahead of the MMAs)
   // render_tc2 with the halving pyramid fused in (64 x 64 maps, utils.py:280-294): the composed maps of levels 1..pyr_levels
-  // ([N,K,32,32], [N,K,16,16]) leave the same launch
-  void* pyr[2]; int pyr_levels; int pyr_dbg;
+  // ([N,K,32,32], [N,K,16,16], [N,K,8,8]) leave the same launch
+  void* pyr[3]; int pyr_levels; int pyr_dbg;
 };
 
 // First tile of CTA i's range under the equal-shares schedule.

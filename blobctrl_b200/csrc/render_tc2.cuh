@@ -100,9 +100,11 @@ __device__ __forceinline__ void drain16(OT* oc, size_t P, const uint32_t* e, con
 // array hs[slot][k][tile row] (hand-over by mbarriers hs_full / hs_free); three extra warps (the places of the B ring's
 // staging warps; one warp alone needs longer than a tile: shuffle / convert chains at one warp's issue rate) turn the tile's four image
 // rows into two level-1 rows and one level-2 row — exact 2x2 means, rounded between levels like the reference's repeated
-// interpolate.  Level 3 needs two tiles (eight image rows), which equal tile ranges split between CTAs: a cross-CTA
+// interpolate.  Level 3 needs two tiles (eight image rows), which equal tile ranges split between CTAs.  A cross-CTA
 // hand-over (arrival counter + __threadfence) was measured at +18 us .. +60 us on cfg3's level 64 — MEMBAR.GPU in an SM
-// whose store queue is saturated waits for the whole queue — so level 3 is one more (tiny) pyramid launch on level 2.
+// whose store queue is saturated waits for the whole queue.  Instead the CTA whose range starts on the odd tile of a pair
+// composites the even tile once more as a ghost (stages 1+2 only, ~1 us of the compute warps' slack), so every pair's
+// level-3 row is made inside one CTA.
 template <typename OT, int kP, bool kFromScores, bool kRing, bool kPyr = false>
 __global__ void __launch_bounds__((13 + (kRing ? kTcStageWarps : 0) + (kPyr ? 3 : 0)) * 32, 1)
 render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
@@ -125,6 +127,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(coef + kTcMaxBlobs + 1);
   uint64_t* const hs_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(bars) + ((sizeof(TcBarriers) + 15) & ~(size_t)15));   // kPyr: full[2], free[2]
   float* const hs = reinterpret_cast<float*>(hs_bar + 4);                                                                // kPyr: [2][K][128]
+  float* const l3h = hs + (size_t)2 * p0.K * kTcTileM;                                                                   // kPyr: [K][8] level-3 half-sums of a pair's even tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == kMmaWarp) {
@@ -226,7 +229,12 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
       OT* comp = (p.composed && chunk == 0) ? reinterpret_cast<OT*>(p.composed) + (size_t)n * p.K * P : nullptr;
       float* const my_e = stash + (size_t)row * srow + kTcKOff;   // my_e[k] = plane k of the even pixel
       float* const my_o = my_e + (size_t)kTcTileM * srow;
-      for (int t = 0; t < ntiles; ++t, ++tile_it) {
+      // kPyr with level 3: a level-3 row needs a PAIR of tiles; when this CTA's range starts on the odd tile of a pair, it
+      // first composites the even tile as a ghost (t = -1: stages 1+2 into the pyramid staging only — no composed-map
+      // stores, no A operand), so the pair's level-3 row is made here and no cross-CTA hand-over exists
+      const int t_first = (kPyr && !kFromScores && p.pyr_levels >= 3 && p.composed && chunk == 0 && (t_lo & 1)) ? -1 : 0;
+      for (int t = t_first; t < ntiles; ++t) {
+        const bool ghost = t < 0;
         const int pix0 = (t_lo + t) * kTc2TilePx + 2 * row;
         const bool live = pix0 < P;                           // P even: both pixels or none
         const int y = live ? pix0 / p.W : 0;
@@ -249,7 +257,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
           }
         } else {
           float Ta = 1.0f, Tb = 1.0f;
-          const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE;
+          const bool wr = comp != nullptr && live && !BS_ABL_NO_COMP_STORE && !ghost;
           const bool wr_now = wr && half == 0;
           OT* const comp_px = comp + pix0;
           const bool do_pyr = kPyr && comp != nullptr && p.pyr_levels > 0;          // CTA-uniform
@@ -328,7 +336,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
           }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // quarter's stash rows complete
-
+        if (!ghost) {
         if (tile_it > 0) mbar_wait(&bars->a_free[0], (tile_it - 1) & 1);   // previous tile's MMAs have read A
         tc_fence_after();
         const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
@@ -349,6 +357,8 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         tc_fence_before();
         mbar_arrive(&bars->a_full[0]);
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner has read the stash
+        ++tile_it;
+        }
         if constexpr (kPyr) {
           if (comp != nullptr && p.pyr_levels > 0) {           // this warp's half-sums of the tile are staged
             __syncwarp();
@@ -428,10 +438,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
       // ============================ fused pyramid: staged half-sums -> level 1 / 2 / 3 rows ============================
       if constexpr (kPyr) {
         if (p.composed != nullptr && chunk == 0 && p.pyr_levels > 0) {
-          for (int t = 0; t < ntiles; ++t, ++pyr_it) {
+          const int t_first = (p.pyr_levels >= 3 && (t_lo & 1)) ? -1 : 0;      // the ghost tile (see the compute warps)
+          for (int t = t_first; t < ntiles; ++t, ++pyr_it) {
+            const bool ghost = t < 0;
             mbar_wait(&hs_bar[pyr_it & 1], (uint32_t)((pyr_it >> 1) & 1));
             const float* const H = hs + (size_t)(pyr_it & 1) * p.K * kTcTileM;
             const int tt = t_lo + t;                           // tile of the image: rows 4 tt .. 4 tt + 3
+            OT* const l3 = p.pyr_levels >= 3 ? reinterpret_cast<OT*>(p.pyr[2]) + (size_t)n * p.K * 64 + (tt >> 1) * 8 + (lane >> 2) : nullptr;
             // four planes per step: one warp carries the whole tile, so the load -> mean -> round -> shuffle chains of
             // independent planes have to overlap
             OT* const l1 = reinterpret_cast<OT*>(p.pyr[0]) + (size_t)n * p.K * 1024 + (2 * tt) * 32 + lane;
@@ -448,7 +461,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
 #pragma unroll
               for (int u = 0; u < kU; ++u) {
                 const int k = k0 + u;
-                const bool ok = k < p.K && !(p.pyr_dbg & 2);
+                const bool ok = k < p.K && !(p.pyr_dbg & 2) && !ghost;   // a ghost tile's level-1/2 rows belong to the CTA that owns it
                 const float n0 = __shfl_down_sync(0xffffffffu, v0[u], 1), n1 = __shfl_down_sync(0xffffffffu, v1[u], 1);
                 store_px2<OT>(l1 + (size_t)k * 1024, v0[u], n0, ok && (lane & 1) == 0);
                 store_px2<OT>(l1 + (size_t)k * 1024 + 32, v1[u], n1, ok && (lane & 1) == 0);
@@ -458,6 +471,19 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
                   const float w2 = round_to<OT>(0.5f * g0 + 0.5f * g1);                       // level 2, row tt, x = lane >> 1
                   const float w2n = __shfl_down_sync(0xffffffffu, w2, 2);
                   store_px2<OT>(l2 + (size_t)k * 256, w2, w2n, ok && (lane & 3) == 0);
+                  if (l3 != nullptr) {
+                    // level 3 (x = lane >> 2): the even tile of a pair leaves its horizontal half-sums in l3h (this warp's own
+                    // planes: no hand-over); the odd tile adds its own and writes the row
+                    const float h = 0.5f * w2 + 0.5f * __shfl_xor_sync(0xffffffffu, w2, 2);
+                    float* const slot = l3h + min(k, p.K - 1) * 8 + (lane >> 2);
+                    if ((tt & 1) == 0) {
+                      if ((lane & 3) == 0 && k < p.K) *slot = h;
+                    } else {
+                      const float w3 = round_to<OT>(0.5f * *slot + 0.5f * h);
+                      const float w3n = __shfl_down_sync(0xffffffffu, w3, 4);
+                      store_px2<OT>(l3 + (size_t)k * 64, w3, w3n, k < p.K && (lane & 7) == 0);
+                    }
+                  }
                 }
               }
             }
@@ -496,7 +522,7 @@ static inline Tc2Plan plan_tc2(int K, int C, bool pyr = false) {
   if (K - 1 > kTcMaxBlobs || C < 1) return pl;
   pl.Kp = round_up(K + kTcKOff, 16);
   const size_t fixed = (size_t)2 * (pl.Kp + 4) * kTcTileM * 4 + 2 * kTcTileM * 4 + (kTcMaxBlobs + 1) * sizeof(BlobCoef) +
-                       sizeof(TcBarriers) + 512 + (pyr ? (size_t)2 * K * kTcTileM * 4 + 64 : 0);   // + fused pyramid: hand-over barriers, hs[2][K][128]
+                       sizeof(TcBarriers) + 512 + (pyr ? (size_t)2 * K * kTcTileM * 4 + (size_t)K * 32 + 64 : 0);   // + fused pyramid: barriers, hs[2][K][128], l3h[K][8]
   const size_t per_c = (size_t)pl.Kp * 2;
   if (fixed + per_c * 32 > kTcSmemBudget) return pl;
   int c_tile = std::min(kTcMaxCTile, round_up(C, 32));
