@@ -73,7 +73,8 @@ typedef enum {
   BLOBSPLAT_ENGINE_AUTO = 0,
   BLOBSPLAT_ENGINE_FMA = 1,    /* CUDA-core FP32/FP64 FMA tiles */
   BLOBSPLAT_ENGINE_TENSOR = 2, /* tcgen05 MMA, weights staged into tensor memory by threads (bf16/f16: kind::f16; f32: split precision) */
-  BLOBSPLAT_ENGINE_TMA = 3     /* 16-bit maps only: operands by TMA loads, tcgen05 MMA from shared memory, output by TMA stores */
+  BLOBSPLAT_ENGINE_TMA = 3     /* 16-bit maps only (16-byte aligned, pixel-contiguous, H*W and C multiples of 8, K <= 256): operands by
+                                  TMA loads, tcgen05 MMA from shared memory, 128-byte line stores; whole pyramids per launch */
 } blobsplat_engine;
 
 typedef struct {
@@ -179,10 +180,11 @@ BLOBSPLAT_API int blobsplat_feature_splat(const void* scores, int64_t stride_n, 
  *      contraction as (3) for n_levels score maps of one batch (same N, K, dtype; per-level H, W, C), i.e. the loop
  *      `for s in sizes: splat_features_from_scores(scores_pyramid[s], features[s], s)` over the pyramid returned by
  *      splat_features (utils.py:235-241, 57-77).  All arrays are HOST arrays of n_levels entries (pointers are
- *      device pointers).  engine AUTO / FMA: level by level exactly as (3).  engine TENSOR: when every level is
- *      a dense contraction with the same operand tiling (2..4 levels, C[i] >= 64 with one
- *      common channel tile) the levels run as ONE tcgen05 launch over the concatenated tile sequence, otherwise
- *      level by level on the tensor engine.
+ *      device pointers).  engine FMA: level by level exactly as (3).  engine TMA, and AUTO for 16-bit pyramids
+ *      that are real contractions (2..4 levels, K >= 12, C[i] >= 64, maps inside the TMA envelope): ONE launch of the
+ *      TMA engine over all levels.  engine TENSOR: when every level shares an operand tiling (2..4 levels,
+ *      C[i] >= 64 with one common channel tile) ONE launch of the thread-staged tensor engine over the concatenated
+ *      tile sequence, otherwise level by level.  AUTO otherwise: level by level as (3).
  */
 BLOBSPLAT_API int blobsplat_feature_splat_levels(int n_levels, const void* const* scores, const int64_t* stride_n,
                               const int64_t* stride_k, const int64_t* stride_p, const void* const* features,
@@ -258,8 +260,9 @@ BLOBSPLAT_API int blobsplat_render(const float* xs, const float* ys, const float
  *      splat_features_from_scores per level (utils.py:57-77).  HOST arrays of n_levels (1..4) entries:
  *      features[l] [N, M+1, C[l]] (NULL = level wanted as maps only), composed[l] [N, M+1, S>>l, S>>l] (required: the
  *      pyramid is an output, utils.py:235-241), grids[l] [N, C[l], S>>l, S>>l].  float32 parameters; float32 /
- *      bfloat16 / float16 features and maps of one dtype.  Same launches as calling (4), (2b), (3b) in sequence — it
- *      exists because at small batches the host's per-call overhead, not the GPU, bounds that sequence.
+ *      bfloat16 / float16 features and maps of one dtype.  Same results, bit for bit, as calling (4), (2b), (3b) in sequence.
+ *      Fewer launches: for S == 64 in 16 bits the pyramid leaves the render launch itself (render_tc2.cuh, kPyr) and the
+ *      lower levels are one launch of the TMA engine — two launches for BlobNet's four resolutions.
  */
 BLOBSPLAT_API int blobsplat_render_multiscale(const float* xs, const float* ys, const float* covs, const float* sizes,
                               int N, int M, int S, int n_levels, const void* const* features, const int* C,
