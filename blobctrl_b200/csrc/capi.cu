@@ -56,6 +56,14 @@ int render_tc_supported(int K, int C, int H, int W, int feat_dtype, int out_dtyp
 void render_tc_limits(int* max_k, int* c_multiple, int* max_c);
 
 constexpr int kMaxBlobs = 1 << 20;
+// BLOBSPLAT_F32_EXACT=1 (read per call): float32 stage 3 stays on the CUDA-core FMA engine under AUTO — full fp32 products
+// and sums like the reference's einsum — and the fused tensor-core render reports "unsupported", so splat_features takes
+// its scores + FMA-splat path.  Default off: the split-precision tensor paths are within 1e-6 of scale (bar: 1e-5).
+static inline bool f32_exact() {
+  const char* e = std::getenv("BLOBSPLAT_F32_EXACT");
+  return e && e[0] == '1';
+}
+
 #ifndef BS_TMA_LEVELS_AUTO
 #define BS_TMA_LEVELS_AUTO 1     // AUTO runs 16-bit pyramids on the TMA engine (splat_tma.cu)
 #endif
@@ -212,7 +220,8 @@ int blobsplat_feature_splat(const void* scores, int64_t stride_n, int64_t stride
   // splat of 16 images; 16-bit products are exact in the fp32 accumulator, so K = 1 stays bit-identical).  float32
   // keeps small K on the FMA engine: a single product is exact there, 3xTF32 is not.
   const bool big = dtype != BLOBSPLAT_F32 && (long long)N * C * H * W >= (1ll << 24);
-  if (tc_ok && (engine == BLOBSPLAT_ENGINE_TENSOR || (engine == BLOBSPLAT_ENGINE_AUTO && C >= 64 && (K >= 12 || big))))
+  const bool exact = dtype == BLOBSPLAT_F32 && f32_exact();
+  if (tc_ok && (engine == BLOBSPLAT_ENGINE_TENSOR || (engine == BLOBSPLAT_ENGINE_AUTO && !exact && C >= 64 && (K >= 12 || big))))
     return feature_splat_tc_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
                                      (cudaStream_t)stream);
   return feature_splat_fma_dispatch(scores, stride_n, stride_k, stride_p, features, out, N, K, C, H, W, dtype,
@@ -338,6 +347,7 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
   BS_CHECK_ARG(features && grid, "NULL pointer");
   const char* why = nullptr;
   if (!render_tc_supported(M + 1, C, H, W, feat_dtype, out_dtype, &why)) BS_UNSUPPORTED("fused render: %s", why);
+  if (out_dtype == BLOBSPLAT_F32 && f32_exact()) BS_UNSUPPORTED("fused render: BLOBSPLAT_F32_EXACT=1 keeps float32 on the FMA engine");
   DeviceGuard g(device);
   if (g.status) return g.status;
   return render_tc_dispatch(xs, ys, covs, sizes, features, feat_dtype, N, M, H, W, C, composed, grid, out_dtype,

@@ -1042,3 +1042,24 @@ def test_fused_pyramid_equals_the_pyramid_kernel(n, m, c, levels, dtype):
     torch.cuda.synchronize()
     for l in range(1, levels):
         assert torch.equal(comps[l], pyr[64 >> l]), f"graph replay: level {64 >> l}"
+
+
+def test_f32_exact_switch_keeps_float32_on_the_fma_engine(monkeypatch):
+    """BLOBSPLAT_F32_EXACT=1: float32 stage 3 under AUTO runs on the FMA engine — bit-identical to
+    engine='fma' — and splat_features gives the scores + FMA-splat result instead of the split-precision fused render."""
+    from blobctrl_b200 import ops
+    syn = blob_oracle.synthetic_blobs(3, 20, seed=9, c=96)
+    b = _blob(syn)
+    feats = torch.from_numpy(syn["features"]).to(DEV)
+    sc, _ = ops.render_scores(b["xs"], b["ys"], b["covs"], b["sizes"], 32, 32)
+    fma = ops.feature_splat(sc, feats, engine="fma")
+    auto_default = ops.feature_splat(sc, feats)
+    monkeypatch.setenv("BLOBSPLAT_F32_EXACT", "1")
+    auto_exact = ops.feature_splat(sc, feats)
+    assert torch.equal(auto_exact, fma)
+    got = _impl().splat_features(**b, features=feats, score_size=32, interp_size=32, ret_layout=False)
+    assert torch.equal(got["feature_grid"], fma)
+    monkeypatch.delenv("BLOBSPLAT_F32_EXACT")
+    want = blob_oracle.splat_features(**syn, score_size=32, interp_size=32, dtype=np.float64, ret_layout=False)
+    close_scaled(_np(auto_default), want["feature_grid"], 1e-5, "default AUTO (tensor engine)")
+    close_scaled(_np(fma), want["feature_grid"], 1e-5, "FMA engine")
