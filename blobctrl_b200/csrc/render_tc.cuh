@@ -147,6 +147,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (((++spins) & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// Busy wait (mbarrier.test_wait, no hardware suspend): for single-thread roles (TMA producer, MMA issue) whose hand-overs are on
+// the critical path of every tile — a suspended try_wait wakes up several hundred cycles after the phase flips.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0, spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if (((++spins) & 0xffffu) == 0) {
+      if (t0 == 0) t0 = clock64();
+      else if (clock64() - t0 > 4000000000ll) __trap();
+    }
+  }
+}
+#ifndef BS_MMA_SPIN
+#define BS_MMA_SPIN 0          // fused kernels: the MMA-issuing thread busy-waits on its barriers (measured at cfg5b, sustained: 1.358 vs 1.314 ms suspended — spinning costs power)
+#endif
+#ifndef BS_DRAIN_SPIN
+#define BS_DRAIN_SPIN 0        // the drain warps busy-wait for their accumulators (1.417 ms: worse still)
+#endif
+__device__ __forceinline__ void mbar_wait_mma(uint64_t* bar, uint32_t parity) {
+  if (BS_MMA_SPIN) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void mbar_wait_drain(uint64_t* bar, uint32_t parity) {
+  if (BS_DRAIN_SPIN) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -896,7 +924,7 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
         const bool live = pix < P;
 #pragma unroll 1
         for (int h = 0; h < n_parts; ++h) {
-          mbar_wait(&bars->d_full[h], tile_it & 1);
+          mbar_wait_drain(&bars->d_full[h], tile_it & 1);
           if (q == 0 && tile_it == 0) TC_STAMP(5 + h);   // first D half ready
           tc_fence_after();
           if constexpr (kH2) { if (t == 0 && h == 0) inv = bars->unit_inv[unit_it & 7]; }   // staged before the unit's first MMA
@@ -975,14 +1003,14 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
                                           (kSplit == 0 && BS_B_NMAJOR) ? 1u : 0u);
         const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_stride);
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
-        mbar_wait(&bars->b_full[buf], rnd & 1);
+        mbar_wait_mma(&bars->b_full[buf], rnd & 1);
         for (int t = 0; t < ntiles; ++t, ++tile_it) {
           const int abuf = a_bufs == 2 ? (tile_it & 1) : 0, ause = a_bufs == 2 ? (tile_it >> 1) : tile_it;
-          mbar_wait(&bars->a_full[abuf], ause & 1);
+          mbar_wait_mma(&bars->a_full[abuf], ause & 1);
           tc_fence_after();
           const uint32_t tmem_a = tmem_a0 + (uint32_t)abuf * a_buf_cols;
           for (int h = 0; h < n_parts; ++h) {
-            if (tile_it > 0) mbar_wait(&bars->d_empty[h], (tile_it - 1) & 1);
+            if (tile_it > 0) mbar_wait_mma(&bars->d_empty[h], (tile_it - 1) & 1);
             tc_fence_after();
             const uint32_t d_addr = tmem + (uint32_t)(h * c_half);
             uint32_t acc = 0;

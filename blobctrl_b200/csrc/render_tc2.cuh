@@ -378,7 +378,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
 #pragma unroll 1
         for (int j = 0; j < nsub; ++j, ++sub_it) {
           const int slot = sub_it & 1;
-          mbar_wait(&bars->d_full[slot], (sub_it >> 1) & 1);
+          mbar_wait_drain(&bars->d_full[slot], (sub_it >> 1) & 1);
           tc_fence_after();
           const uint32_t te = tmem + lane_addr + (uint32_t)(slot * 2 * cw), to = te + (uint32_t)cw;
           OT* const o = out + (size_t)(j * cw) * P + pix0;
@@ -408,13 +408,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
         const uint32_t idesc = make_idesc(std::is_same<OT, __half>::value ? 0u : 1u, (uint32_t)cw, 1u);
         const uint32_t b_base = smem_u32(b_smem + (size_t)buf * b_bytes);
         const uint32_t lbo = (uint32_t)p.c_tile * 16u, sbo = 128u;
-        mbar_wait(&bars->b_full[buf], rnd & 1);
+        mbar_wait_mma(&bars->b_full[buf], rnd & 1);
         for (int t = 0; t < ntiles; ++t, ++tile_it) {
-          mbar_wait(&bars->a_full[0], tile_it & 1);
+          mbar_wait_mma(&bars->a_full[0], tile_it & 1);
           tc_fence_after();
           for (int j = 0; j < nsub; ++j, ++sub_it) {
             const int slot = sub_it & 1;
-            if (sub_it >= 2) mbar_wait(&bars->d_empty[slot], ((sub_it >> 1) - 1) & 1);
+            if (sub_it >= 2) mbar_wait_mma(&bars->d_empty[slot], ((sub_it >> 1) - 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int par = 0; par < 2; ++par) {

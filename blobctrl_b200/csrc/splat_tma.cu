@@ -104,22 +104,6 @@ __device__ __forceinline__ StItem st_decode(const StParams& p, int item, int& le
   return it;
 }
 
-// Busy wait (mbarrier.test_wait, no hardware suspend): for the single producer / MMA threads, whose hand-overs are on
-// the critical path of every item — a suspended try_wait wakes up several hundred cycles after the phase flips.
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-  const uint32_t a = smem_u32(bar);
-  uint32_t ok = 0, spins = 0;
-  long long t0 = 0;
-  while (true) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    if (ok) return;
-    if (((++spins) & 0xffffu) == 0) {
-      if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 4000000000ll) __trap();
-    }
-  }
-}
 // Walks the item sequence (group fastest, then tile, image, level) without per-item divisions: the producer and MMA
 // roles are single threads, where a decode with three integer divisions costs several hundred cycles per item.
 struct StIter {

@@ -7,9 +7,7 @@ import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "r2_all": "",
-    "r2_noparts": "-DBS_D_PARTS=0", "r2_abuf1": "-DBS_A_BUFS=1", "r2_noalign": "-DBS_ALIGNED_SPLIT=0",
-    "r2_base": "-DBS_D_PARTS=0 -DBS_A_BUFS=1 -DBS_ALIGNED_SPLIT=0",
+    "r3_susp": "-DBS_MMA_SPIN=0", "r3_mma_spin": "-DBS_MMA_SPIN=1", "r3_all_spin": "-DBS_MMA_SPIN=1 -DBS_DRAIN_SPIN=1",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 
