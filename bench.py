@@ -536,10 +536,27 @@ def variants(B, ops, dev, peak):
     chans = {64: 320, 32: 640, 16: 1280, 8: 1280}
     g = torch.Generator().manual_seed(1)
     lf = {s: torch.randn(64, 33, c, generator=g).to(dev).to(torch.bfloat16) for s, c in chans.items()}
-    ms = timed(lambda: B.splat_features_multiscale(**blobs, score_size=64, level_features=lf, out_dtype=torch.bfloat16))
+    ms = timed(lambda: B.splat_features_multiscale(**blobs, score_size=64, level_features=lf, out_dtype=torch.bfloat16), reps=50, warm=5)
     by = 64 * (28 * 32 + sum(33 * c * 2 + 33 * s * s * 2 + c * s * s * 2 for s, c in chans.items()))
     out["cfg3_multiscale_bf16"] = {"ms": ms, "Mpxblob_s": 64 * 32 * sum(s * s for s in chans) / ms / 1e3,
-                                   "GBs": by / ms / 1e6, "frac": by / ms / 1e6 / peak}
+                                   "GBs": by / ms / 1e6, "frac": by / ms / 1e6 / peak,
+                                   "launches": ["render_tc2<kPyr> (stages 1+2+3 at 64x64 + pyramid levels 32/16/8)",
+                                                "splat_tma (stage 3 at 32/16/8, TMA operands)"],
+                                   "what": "ONE call (blobsplat_render_multiscale), eager; graph_ms = the same call as a CUDA graph"}
+    # stage 3 alone at the cfg5c shape (1024 images, K = 65, C = 320, bf16) on the TMA engine vs the thread-staged tensor engine
+    try:
+        sc5 = torch.rand(N_IMG, M_BLOBS + 1, SIZE, SIZE, device=dev)
+        sc5 = (sc5 / sc5.sum(1, keepdim=True)).to(torch.bfloat16)
+        f5 = torch.randn(N_IMG, M_BLOBS + 1, CHANNELS, device=dev).to(torch.bfloat16)
+        by5 = N_IMG * ((M_BLOBS + 1) * (CHANNELS + P) * 2 + CHANNELS * P * 2)
+        s3 = {}
+        for eng in ("tma", "tensor"):
+            ms5 = timed(lambda: ops.feature_splat(sc5, f5, engine=eng))
+            s3[eng] = {"ms": ms5, "GBs": by5 / ms5 / 1e6, "frac": by5 / ms5 / 1e6 / peak}
+        out["cfg5c_stage3_only_bf16"] = s3
+        del sc5, f5
+    except Exception as e:  # pragma: no cover
+        out["cfg5c_stage3_only_bf16"] = {"error": str(e)[:200]}
     # latency-bound configs: report microseconds.  eager = the reference-signature call; graph = the same call with
     # cuda_graph=True (one cudaGraphLaunch per call, blobctrl_b200/graphs.py); reference_* = the UNMODIFIED reference
     # function (baseline/_ref) on the host CPU as its scripts run it, and its ~20-launch ATen sequence on this GPU

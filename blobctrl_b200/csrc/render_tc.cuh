@@ -84,6 +84,9 @@
 #ifndef BS_ALIGNED_SPLIT
 #define BS_ALIGNED_SPLIT 1      // split the blobs on an operand k-group boundary: one pair barrier per tile instead of three
 #endif
+#ifndef BS_SKIP_UNIT_SCALE
+#define BS_SKIP_UNIT_SCALE 1    // kSplit = 2: no per-unit feature scale when max|f| is in [0.5, 4096)
+#endif
 #ifndef BS_MAX_B
 #define BS_MAX_B 4             // B operand ring depth (1 = staged by the compute warps between units)
 #endif
@@ -423,6 +426,10 @@ __device__ __forceinline__ void tc_stage_b(const RenderTcParams& p, int n, int c
     int e = 0;
     if (mx > 0.0f && mx < 3.0e38f) (void)frexpf(mx, &e);                            // mx = m * 2^e, m in [0.5, 1)
     e = max(-100, min(100, e));
+    // Units whose magnitude already sits in [0.5, 4096) stay unscaled: fp16 holds them without overflow and the absolute
+    // resolution 2^-24 is <= 2^-23 of the unit's magnitude either way — and the drain skips its 2 multiplies per stored pair
+    // (1 280 FMUL of the 14 400 warp instructions of a BlobNet tile; typical features are O(1)).
+    if (BS_SKIP_UNIT_SCALE && mx >= 0.5f && mx < 4096.0f) e = 0;
     const float scale = exp2f((float)-e);
     if (tid == 0) sc->unit_inv[unit & 7] = exp2f((float)e);
     // features [K, C] -> K-major operand rows, x = f * scale split into x1 = fp16(x), x2 = fp16(x - x1).  One thread moves
@@ -945,11 +952,13 @@ __global__ void __launch_bounds__((4 * kHalves + 5 + (kRing ? kTcStageWarps : 0)
               tmem_wait_ld();
               for (int cc = 0; cc < c_half; cc += 64) {
                 if (cc + 32 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 32, rb); tmem_ld_16x32bx2_x16(tb + cc + 32, rb + 16); }
-                store_pixel_pairs<kH2>(o2 + (size_t)cc * P, (size_t)P, ra, live2, inv);
+                if (kH2 && inv != 1.0f) store_pixel_pairs<true>(o2 + (size_t)cc * P, (size_t)P, ra, live2, inv);
+                else store_pixel_pairs<false>(o2 + (size_t)cc * P, (size_t)P, ra, live2, inv);
                 tmem_wait_ld();
                 if (cc + 32 < c_half) {
                   if (cc + 64 < c_half) { tmem_ld_16x32bx2_x16(taddr + cc + 64, ra); tmem_ld_16x32bx2_x16(tb + cc + 64, ra + 16); }
-                  store_pixel_pairs<kH2>(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2, inv);
+                  if (kH2 && inv != 1.0f) store_pixel_pairs<true>(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2, inv);
+                  else store_pixel_pairs<false>(o2 + (size_t)(cc + 32) * P, (size_t)P, rb, live2, inv);
                   tmem_wait_ld();
                 }
               }

@@ -7,7 +7,7 @@ import ctypes, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "r3_susp": "-DBS_MMA_SPIN=0", "r3_mma_spin": "-DBS_MMA_SPIN=1", "r3_all_spin": "-DBS_MMA_SPIN=1 -DBS_DRAIN_SPIN=1",
+    "r3_unit_scale": "-DBS_SKIP_UNIT_SCALE=0", "r3_skip_scale": "-DBS_SKIP_UNIT_SCALE=1",
 }
 VDIR = os.path.join(ROOT, "blobctrl_b200", "lib", "variants")
 

@@ -1063,3 +1063,21 @@ def test_f32_exact_switch_keeps_float32_on_the_fma_engine(monkeypatch):
     want = blob_oracle.splat_features(**syn, score_size=32, interp_size=32, dtype=np.float64, ret_layout=False)
     close_scaled(_np(auto_default), want["feature_grid"], 1e-5, "default AUTO (tensor engine)")
     close_scaled(_np(fma), want["feature_grid"], 1e-5, "FMA engine")
+
+
+@pytest.mark.parametrize("scale", [1.0, 3e-5, 0.3, 700.0, 5000.0, 2e7])
+def test_fused_float32_render_across_feature_magnitudes(scale):
+    """2xFP16 split of float32 maps: features of a unit are pre-scaled by a power of two only when max|f| lies outside
+    [0.5, 4096) (render_tc.cuh, tc_stage_b) — both branches, and a mix of magnitudes across images, at the 1e-5 bar."""
+    from blobctrl_b200 import ops
+    n, m, c = 6, 40, 128
+    syn = blob_oracle.synthetic_blobs(n, m, seed=21, c=c)
+    per_image = np.array([scale, scale * 3.0, 1.0, scale, 1e-3, scale * 0.1], dtype=np.float32).reshape(n, 1, 1)
+    syn["features"] = (syn["features"] * per_image).astype(np.float32)
+    b = _blob(syn)
+    feats = torch.from_numpy(syn["features"]).to(DEV)
+    comp, grid = ops.render_fused(b["xs"], b["ys"], b["covs"], b["sizes"], feats, 32, 32)
+    want = blob_oracle.splat_features(**syn, score_size=32, interp_size=32, dtype=np.float64, ret_layout=False)
+    got, ref = _np(grid), want["feature_grid"]
+    for i in range(n):                                  # per image: each has its own magnitude
+        close_scaled(got[i], ref[i], 1e-5, f"image {i} (feature scale {float(per_image[i, 0, 0]):g})")
