@@ -969,6 +969,7 @@ def test_cfg4_edit_loop_latent_parity_toy_width(dtype):
     (2, 65, [(64, 64, 320), (32, 32, 640)]),                                   # Kp = 80: shallower rings
     (2, 5, [(24, 24, 72), (12, 12, 136), (4, 4, 8)]),                          # ragged pixel and channel tails, 16-pixel image
     (1, 128, [(48, 40, 200)]),                                                 # K = 128 (the thread-staged engine stops at 127 blobs + bg)
+    (1, 256, [(16, 16, 64), (8, 8, 136)]),                                     # K = 256: the TMA box limit (16 MMA k-steps)
     (5, 33, [(8, 8, 64), (4, 2, 1280)]),                                       # 8-pixel image: one 16-column MMA
     (2, 40, [(20, 18, 328), (10, 12, 96), (64, 64, 320), (2, 4, 64)])])        # four levels of unrelated shapes
 def test_tma_engine_vs_oracle(n, k, levels, dtype, rel):
@@ -993,9 +994,14 @@ def test_tma_engine_vs_oracle(n, k, levels, dtype, rel):
 
 def test_tma_engine_views_and_envelope():
     """Strided score views are consumed in place; shapes outside the TMA envelope raise BlobSplatUnsupported on request and
-    fall back to the other engines under AUTO."""
+    fall back to the other engines under AUTO; empty batches are no-ops."""
     from blobctrl_b200 import ops, _capi as C
     g = torch.Generator().manual_seed(5)
+    empty = ops.feature_splat_levels([torch.empty(0, 17, 8, 8, device=DEV, dtype=torch.bfloat16)] * 2,
+                                     [torch.empty(0, 17, 64, device=DEV, dtype=torch.bfloat16)] * 2, engine="tma")
+    assert [tuple(t.shape) for t in empty] == [(0, 64, 8, 8)] * 2
+    with pytest.raises(C.BlobSplatUnsupported):        # K = 257 > one TMA box
+        ops.feature_splat(torch.rand(1, 257, 8, 8, device=DEV).bfloat16(), torch.randn(1, 257, 64, device=DEV).bfloat16(), engine="tma")
     big = torch.rand(2, 20, 40, 32, generator=g).to(DEV).to(torch.bfloat16)
     view = big[:, 2:19, :32, :]                          # plane stride 1280 > 1024 pixels, image stride 20 planes
     ft = torch.randn(2, 17, 256, generator=g).to(DEV).to(torch.bfloat16)
