@@ -218,7 +218,7 @@ def kernel_source_sha():
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "blobctrl_b200", "csrc")
-    for f in ("common.cuh", "render_tc.cuh", "render_tc2.cuh", "render_tc.cu"):
+    for f in ("common.cuh", "render_tc.cuh"):      # the float32 fused kernel lives in these two (render_tc2.cuh: 16-bit only)
         h.update(open(os.path.join(csrc, f), "rb").read())
     return h.hexdigest()[:16]
 

@@ -21,6 +21,9 @@
 #ifndef BS_CW_MAX
 #define BS_CW_MAX 128          // widest drain sub-step (channels)
 #endif
+#ifndef BS_HEAD_STAGE
+#define BS_HEAD_STAGE 1        // two-pixel kernel without the B ring: the drain warps stage the CTA's first unit
+#endif
 #ifndef BS_PX2
 #define BS_PX2 1               // 16-bit maps: use the two-pixels-per-lane kernel where its preconditions hold
 #endif
@@ -212,10 +215,14 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
       if (unit_it == 0)      // stash columns that are never written stay zero for the whole kernel
         for (int i = ctid; i < 2 * kTcTileM * srow; i += kComputeThreads) stash[i] = 0.0f;
       if constexpr (!kRing) {
-        if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
-        tc_stage_b<OT, OT, false>(p, n, c0, b_smem, b_bytes, ctid, kComputeThreads);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(&bars->b_full[0]);
+        // the CTA's first unit is staged by the drain warps, which have nothing to drain yet: the features' load round trip
+        // leaves the head of the launch (BS_HEAD_STAGE); later units are staged here, behind the previous unit's drain
+        if (!(BS_HEAD_STAGE && unit_it == 0)) {
+          if (unit_it > 0) mbar_wait(&bars->b_free[0], (unit_it - 1) & 1);
+          tc_stage_b<OT, OT, false>(p, n, c0, b_smem, b_bytes, ctid, kComputeThreads);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&bars->b_full[0]);
+        }
       }
       uint32_t any_general;
       asm volatile(
@@ -370,6 +377,13 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
     } else if (warp < kComputeWarps + 4) {
       // ============================ drain: (even, odd) pixel pairs, 32-bit stores ============================
       const int q = warp - kComputeWarps;
+      if constexpr (!kRing) {
+        if (BS_HEAD_STAGE && unit_it == 0) {               // 128 threads for 256 arrivals: two each
+          tc_stage_b<OT, OT, false>(p, n, c0, b_smem, b_bytes, (int)threadIdx.x - kComputeThreads, 128);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], 2;" ::"r"(smem_u32(&bars->b_full[0])) : "memory");
+        }
+      }
       OT* const out = reinterpret_cast<OT*>(p.grid) + ((size_t)n * p.C + c0) * P;
       const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
       for (int t = 0; t < ntiles; ++t, ++tile_it) {
