@@ -26,7 +26,7 @@ int render_tc_pyramid_dispatch(const float* xs, const float* ys, const float* co
   if (!render_tc2_usable(dtype, S, S, composed, grid, nullptr, 0, 0, 1)) return 1;
   for (int l = 0; l < pyr_levels; ++l)
     if (!pyr[l] || (reinterpret_cast<uintptr_t>(pyr[l]) & 15) != 0) return 1;      // bulk stores: 16-byte aligned rows
-  const Tc2Plan pl2 = plan_tc2(M + 1, C, /*pyr=*/true);
+  const Tc2Plan pl2 = plan_tc2(M + 1, C, /*pyr=*/true, (long long)N * 16);
   if (!pl2.ok) return 1;
   RenderTcParams p{};
   p.xs = xs; p.ys = ys; p.covs = covs; p.sizes = sizes; p.feats = features; p.composed = composed; p.grid = grid;
@@ -48,12 +48,16 @@ int render_tc_dispatch(const float* xs, const float* ys, const float* covs, cons
                        int feat_dtype, int N, int M, int H, int W, int C, void* composed, void* grid, int out_dtype,
                        cudaStream_t st) {
   (void)feat_dtype;
-  const TcPlan pl = plan_tc(M + 1, C, split_of(out_dtype));
+  const long long px = (long long)H * W, tiles = N * ((px + kTcTileM - 1) / kTcTileM);
+  int split = split_for_launch(out_dtype, tiles);
+  TcPlan pl = plan_tc(M + 1, C, split, tiles);
+  if (!pl.ok && split == 1) { split = 2; pl = plan_tc(M + 1, C, split, tiles); }     // the TF32 form needs more shared / tensor memory
   if (!pl.ok) BS_UNSUPPORTED("fused render: %s", pl.why);
   RenderTcParams p{};
+  p.f32_split = split;
   p.xs = xs; p.ys = ys; p.covs = covs; p.sizes = sizes; p.feats = features; p.composed = composed; p.grid = grid;
   if (render_tc2_usable(out_dtype, H, W, composed, grid, nullptr, 0, 0, 1)) {   // 16-bit maps: two pixels per lane
-    const Tc2Plan pl2 = plan_tc2(M + 1, C);
+    const Tc2Plan pl2 = plan_tc2(M + 1, C, false, N * ((px + kTc2TilePx - 1) / kTc2TilePx));
     if (pl2.ok) return run_tc2<false>(p, pl2, N, M + 1, H, W, C, out_dtype, st);
   }
   if (int rc = fill_tc_units(p, pl, N, M + 1, H, W, C)) return rc;

@@ -331,6 +331,7 @@ struct RenderTcParams {
   int n_parts;            // the channel tile is accumulated and drained in n_parts parts of c_tile / n_parts channels: the MMAs of
                           // part j of tile t + 1 start as soon as part j of tile t has been drained
   int a_bufs;             // A operand buffers in tensor memory (2: stages 1+2 and the conversion run a tile ahead of the MMAs)
+  int f32_split;          // float32 maps: 1 = 3xTF32, 2 = 2xFP16 (chosen per launch, split_for_launch)
   // render_tc2 with the halving pyramid fused in (64 x 64 maps, utils.py:280-294): the composed maps of levels 1..pyr_levels
   // ([N,K,32,32], [N,K,16,16], [N,K,8,8]) leave the same launch
   void* pyr[3]; int pyr_levels; int pyr_dbg;
@@ -1085,6 +1086,25 @@ static inline int f32_split() {
   return (e && e[0] == 't') ? 1 : 2;
 }
 static inline int split_of(int dtype) { return dtype == BLOBSPLAT_F32 ? f32_split() : 0; }
+// ... and per launch.  A launch with fewer tiles than SMs is all head (one tile per CTA), and the 2xFP16 form's head is
+// longer (per-unit feature maximum before the scaled two-way split): with BS_SMALL_TF32=1 such launches take 3xTF32
+// (cfg2, 1 image x 16 blobs x 320 channels: 12.4 -> 10.3 us as a CUDA graph).  OFF by default: the low bits of an image's
+// result would then depend on how many images share its launch (a chunked render would differ from the whole batch in the
+// seventh digit).  BLOBSPLAT_F32_SPLIT=tf32|fp16 forces one form for every launch.
+#ifndef BS_SMALL_TF32
+#define BS_SMALL_TF32 0
+#endif
+static inline int split_for_launch(int dtype, long long tiles) {
+  if (dtype != BLOBSPLAT_F32) return 0;
+  const char* e = getenv("BLOBSPLAT_F32_SPLIT");
+  if (e && e[0] == 't') return 1;
+  if (e && e[0] == 'f') return 2;
+  static thread_local int cached_dev = -1, sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+    cached_dev = dev;
+  return (BS_SMALL_TF32 && tiles > 0 && tiles < sms) ? 1 : 2;
+}
 
 static inline int tmem_cols_for(int needed) {
   int c = 32;
@@ -1092,7 +1112,27 @@ static inline int tmem_cols_for(int needed) {
   return c;
 }
 
-static inline TcPlan plan_tc(int K, int C, int split) {
+// Small launches (N * tiles per image below the SM count, e.g. one 64 x 64 image = 32 tiles): a narrower channel tile makes
+// more (image, chunk, tile) units, so every SM drains a share of the grid instead of 32 SMs draining all of it; stages 1+2
+// are recomputed per chunk (cheap at these sizes), the composed maps are still written by chunk 0 only.
+// `tiles` = N * tiles per image (0 = do not narrow).  BS_SPREAD_SMALL=0 turns it off.
+#ifndef BS_SPREAD_SMALL
+#define BS_SPREAD_SMALL 1
+#endif
+static inline int spread_c_tile(int c_tile, int C, long long tiles, int floor_c) {
+  if (!BS_SPREAD_SMALL || tiles <= 0) return c_tile;
+  static thread_local int cached_dev = -1, sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev != cached_dev && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess)
+    cached_dev = dev;
+  if (tiles * ((C + c_tile - 1) / c_tile) >= sms) return c_tile;
+  const long long want = (sms + tiles - 1) / tiles;                      // channel chunks for one unit per SM
+  int c = (int)((C + want - 1) / want);
+  c = std::max(floor_c, (c + 31) / 32 * 32);
+  return std::min(c_tile, c);
+}
+
+static inline TcPlan plan_tc(int K, int C, int split, long long tiles = 0) {
   TcPlan pl{};
   pl.ok = false;
   const bool tf32 = split == 1;
@@ -1110,6 +1150,7 @@ static inline TcPlan plan_tc(int K, int C, int split) {
   // prefer a tile that divides C (no ragged chunk)
   for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
     if (C % c == 0) { c_tile = c; break; }
+  c_tile = spread_c_tile(c_tile, C, tiles, 64);
   pl.c_tile = c_tile;
   // as many B buffers as fit (ring, staged ahead by the staging warps); one when B fills shared memory
   pl.nb = (int)std::min<size_t>(BS_MAX_B, (kTcSmemBudget - fixed) / (per_c * c_tile));
@@ -1220,7 +1261,7 @@ static int launch_tc_dtype(const RenderTcParams& p, size_t smem, int out_dtype, 
     if (const char* e = getenv("BLOBSPLAT_TC_HALVES")) { if (e[0] == '1') halves = 1; }
   }
   if (out_dtype == BLOBSPLAT_F32) {
-    if (f32_split() == 1) return launch_tc<float, float, 1, 2, kFromScores>(p, smem, st);            // 3xTF32 (A/B partner)
+    if (p.f32_split == 1) return launch_tc<float, float, 1, 2, kFromScores>(p, smem, st);             // 3xTF32 (small launches, A/B partner)
     if constexpr (!kFromScores) { if (halves == 1) return launch_tc<float, float, 2, 1, kFromScores>(p, smem, st); }
     return launch_tc<float, float, 2, 2, kFromScores>(p, smem, st);
   }

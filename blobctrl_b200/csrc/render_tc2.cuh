@@ -530,7 +530,7 @@ render_tc2_kernel(const __grid_constant__ RenderTcLevels L) {
 // ---- host side ------------------------------------------------------------------------------------------------
 struct Tc2Plan { int Kp, c_tile, cw, nb; size_t smem, b_slot; bool ok; };
 
-static inline Tc2Plan plan_tc2(int K, int C, bool pyr = false) {
+static inline Tc2Plan plan_tc2(int K, int C, bool pyr = false, long long tiles = 0) {
   Tc2Plan pl{};
   pl.ok = false;
   if (K - 1 > kTcMaxBlobs || C < 1) return pl;
@@ -543,6 +543,7 @@ static inline Tc2Plan plan_tc2(int K, int C, bool pyr = false) {
   c_tile = std::min<long long>(c_tile, (long long)((kTcSmemBudget - fixed) / per_c) / 32 * 32);
   for (int c = c_tile; c >= std::max(32, c_tile / 2); c -= 32)
     if (C % c == 0) { c_tile = c; break; }
+  c_tile = spread_c_tile(c_tile, C, tiles, 64);          // small launches: more, narrower units (render_tc.cuh)
   // drain sub-step: the widest multiple of 16 channels that divides the tile and leaves room for two 2*cw-column
   // slots next to the two A operands
   int cw = 0;

@@ -8,13 +8,17 @@ namespace blobsplat {
 
 int feature_splat_tc_dispatch(const void* scores, int64_t sn, int64_t sk, int64_t sp, const void* feats, void* out,
                               int N, int K, int C, int H, int W, int dtype, cudaStream_t st) {
-  const TcPlan pl = plan_tc(K, C, split_of(dtype));
+  const long long px = (long long)H * W, tiles = N * ((px + kTcTileM - 1) / kTcTileM);
+  int split = split_for_launch(dtype, tiles);
+  TcPlan pl = plan_tc(K, C, split, tiles);
+  if (!pl.ok && split == 1) { split = 2; pl = plan_tc(K, C, split, tiles); }     // the TF32 form needs more shared / tensor memory
   if (!pl.ok) BS_UNSUPPORTED("tensor-core feature splat: %s", pl.why);
   if (dtype == BLOBSPLAT_F64) BS_UNSUPPORTED("tensor-core feature splat: float64 runs on the FMA engine");
   RenderTcParams p{};
+  p.f32_split = split;
   p.scores = scores; p.sn = sn; p.sk = sk; p.sp = sp; p.feats = feats; p.grid = out;
   if (render_tc2_usable(dtype, H, W, nullptr, out, scores, sn, sk, sp)) {        // 16-bit maps: two pixels per lane
-    const Tc2Plan pl2 = plan_tc2(K, C);
+    const Tc2Plan pl2 = plan_tc2(K, C, false, N * ((px + kTc2TilePx - 1) / kTc2TilePx));
     if (pl2.ok) return run_tc2<true>(p, pl2, N, K, H, W, C, dtype, st);
   }
   if (int rc = fill_tc_units(p, pl, N, K, H, W, C)) return rc;
