@@ -1,4 +1,4 @@
-// Stage 3 from 16-bit score maps on the asynchronous engines only — TMA in, tcgen05, TMA out.
+// Stage 3 from 16-bit score maps with no thread on the operand path — TMA in, tcgen05 from shared memory, full-line stores out.
 //
 // Replaces splat_features_from_scores (blobctrl/utils/utils.py:57-77; duplicate at
 // blobctrl/pipelines/pipeline_blobnet.py:706-721) for bf16 / f16 maps, one level or a whole pyramid
@@ -13,14 +13,15 @@
 //   stride): no thread touches an operand, rows k >= K, channels >= C and pixels >= P arrive as zeros (out-of-bounds
 //   fill).  [A first version used 16-byte boxes into the no-swizzle layout: correct, but 8x the TMA requests.]
 //   D (fp32, TMEM): lane = channel, column = pixel.  A drain thread therefore holds CONSECUTIVE PIXELS of one channel
-//   plane: it packs them to 16 bits, writes 16-byte chunks into a 128B-swizzled staging box (conflict-free) and one
-//   lane per warp hands the box (32 channels x 64 pixels = 32 full 128-byte lines) to the TMA unit, which also clips
-//   ragged channel / pixel tails.  Per 64 KB of output a drain warp issues ~100 instructions; the global store stream is
-//   the TMA engine's.
+//   plane: it packs them to 16 bits and writes 16-byte chunks into a 128B-swizzled staging box of 32 channels x 64 pixels
+//   (conflict-free); the warp reads the box back row-wise and stores whole 128-byte lines, four per instruction
+//   (st.global.cs.v4).  Handing the same box to a TMA tensor store instead (BLOBSPLAT_ST_STORE=tma, kept as an A/B path)
+//   is slower: the TMA unit needs ~6 cycles per 128-byte row (profiles/tma_store_bw_r2.txt), and alternating the two paths
+//   (=hybrid) is slower than either (profiles/splat_tma_r2.md).
 //
 // Warp roles (320 threads, 1 CTA/SM, persistent over a cost-balanced contiguous range of items; an item = (level, image,
 // pixel tile, 128-channel group), channel group fastest so a tile's scores stay resident):
-//   warp 0      producer: one thread issues the TMA loads (scores ring of 2, feature ring of up to 4)
+//   warp 0      producer: one thread issues the TMA loads (scores ring of up to 3, feature ring of up to 8)
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue (SS form) + commits
 //   warps 2-9   drain: two groups of four (TMEM lane quarter = warp & 3), each owning one accumulator slot and every
 //               other item; private staging box per warp
@@ -30,6 +31,9 @@
 
 #include "render_tc.cuh"
 
+#ifndef BS_ST_STORE_MODE
+#define BS_ST_STORE_MODE 0     // drain store path: 0 = line stores by the warps, 1 = TMA tensor stores, 2 = alternate (BLOBSPLAT_ST_STORE)
+#endif
 #ifndef BS_ST_OVERHEAD
 #define BS_ST_OVERHEAD 128     // fixed cost of an item in the schedule's cost model, in pixels (swept on cfg3's lower levels:
                                // 0 -> 51 us, 48 -> 37, 96..256 -> 33, 700 -> 37; profiles/splat_tma_r2.md)
@@ -63,7 +67,7 @@ struct alignas(64) StParams {
   long long total_cost;
   int Kp;           // K rounded up to 16
   int nf, ns, nbuf; // feature ring depth, score ring depth, staging boxes per drain warp
-  int tma_store;    // 1: the drain hands its boxes to the TMA unit; 0: reads them back row-wise and stores 128-byte lines itself
+  int tma_store;    // 0: the drain reads its boxes back row-wise and stores 128-byte lines itself; 1: hands them to the TMA unit; 2: alternates
   const void* out_ptr[kStMaxLevels]; int out_C[kStMaxLevels];   // for the direct stores
   int s_bytes, f_bytes;
   int slot_cols;    // accumulator columns per slot (power of two >= the widest tile)
@@ -286,7 +290,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
     const int dw = warp - kStFirstDrainWarp, q = warp & 3, grp = dw >> 2;
     unsigned char* const my_stage = stage + (size_t)dw * p.nbuf * kStBoxBytes;
     const uint32_t lane_addr = ((uint32_t)(q * 32) << 16);
-    int st_it = 0;
+    int st_it = 0, t_it = 0;
     StIter it;
     if (it_begin + grp < it_end) it.init(p, it_begin + grp);
     for (int item = it_begin + grp, item_it = grp; item < it_end; item += 2, item_it += 2) {
@@ -326,11 +330,15 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
       for (int bb = 0; bb < 2; ++bb) {
         const int b = b_lo + bb;
         if (b >= b_hi) break;
-        const int sbuf = p.tma_store ? st_it % p.nbuf : 0;
-        if (p.tma_store && st_it >= p.nbuf) {                    // the TMA store that last read this box has drained it
+        // store path of this box: 0 = line stores by the warp, 1 = TMA tensor store; mode 2 (hybrid) alternates, so the LSU
+        // and the TMA unit each carry half of the bytes (box 0 of the staging ring is the line-store box, 1.. the TMA ring)
+        const bool via_tma = p.tma_store == 1 || (p.tma_store == 2 && (st_it & 1));
+        const int ring0 = p.tma_store == 2 ? 1 : 0, ring = p.nbuf - ring0;
+        const int sbuf = via_tma ? ring0 + t_it % ring : 0;
+        if (via_tma && t_it >= ring) {                           // the TMA store that last read this box has drained it
           if (lane == 0) {
-            if (p.nbuf == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-            else if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (ring == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            else if (ring == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           __syncwarp();
@@ -343,13 +351,14 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
           *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) =
               make_uint4(pk[bb][4 * c], pk[bb][4 * c + 1], pk[bb][4 * c + 2], pk[bb][4 * c + 3]);
         }
-        if (p.tma_store) {
+        if (via_tma) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
             if (!(p.abl & 1)) tma_store_3d(&L.out, smem_u32(box), px_tile + b * kStBoxPx, it.group * kStM + q * kStBoxCh, it.n);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          ++t_it;
         } else {
           // read the box back row-wise: 8 lanes fetch the 8 chunks of one channel row = one whole 128-byte line of the
           // output plane, a warp instruction stores 4 lines
@@ -466,11 +475,12 @@ int splat_tma_dispatch(int n_levels, const void* const* scores, const int64_t* s
   int widest = 16;
   for (int i = 0; i < n_levels; ++i) widest = std::max(widest, (int)std::min<long long>(256, round_up(H[i] * W[i], 16)));
   const char* sm = std::getenv("BLOBSPLAT_ST_STORE");
-  const bool tma_store = sm && std::strcmp(sm, "tma") == 0;    // A/B: hand the drain's boxes to the TMA unit
+  const int store_mode = !sm ? BS_ST_STORE_MODE : (std::strcmp(sm, "tma") == 0 ? 1 : (std::strcmp(sm, "hybrid") == 0 ? 2 : 0));   // A/B knob
+  const bool tma_store = store_mode != 0;
   const StPlan pl = plan_splat_tma(p.Kp, widest, tma_store);
   if (!pl.ok) BS_UNSUPPORTED("TMA feature splat: K = %d does not fit in shared memory", K);
   const CUtensorMapDataType dt = dtype == BLOBSPLAT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  p.n_levels = n_levels; p.nf = pl.nf; p.ns = pl.ns; p.nbuf = pl.nbuf; p.tma_store = tma_store ? 1 : 0; p.is_bf16 = dtype == BLOBSPLAT_BF16;
+  p.n_levels = n_levels; p.nf = pl.nf; p.ns = pl.ns; p.nbuf = pl.nbuf; p.tma_store = store_mode; p.is_bf16 = dtype == BLOBSPLAT_BF16;
   p.f_bytes = p.Kp * kStM * 2;
   int items = 0, max_npx = 16, overhead = BS_ST_OVERHEAD;
   if (const char* e = std::getenv("BLOBSPLAT_ST_OVERHEAD")) overhead = std::max(0, std::atoi(e));
