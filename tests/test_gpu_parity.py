@@ -577,6 +577,16 @@ def test_full_size_config3_properties():
         close_scaled(_np(out["scores_pyramid"][s][sl]), pyr[s], 1e-2, f"cfg3 scores@{s}")
         want = blob_oracle.splat_features_from_scores(pyr[s], _np(feats[s][sl]).astype(np.float64), s, channels_last=False)
         close_scaled(_np(out["feature_grids"][s][sl]), want, 1e-2, f"cfg3 grid@{s}")
+    # the WHOLE batch (every CTA's item range of the TMA engine, every tile pair of the fused pyramid): each grid against the
+    # float64 contraction of the produced 16-bit maps, each pyramid level against the pyramid kernel on the level above
+    for s in chans:
+        want = torch.einsum("nkhw,nkc->nchw", out["scores_pyramid"][s].double(), feats[s].double())
+        err = (out["feature_grids"][s].double() - want).abs().max().item()
+        assert err <= 1e-2 * want.abs().max().item(), f"cfg3 full batch grid@{s}: {err}"
+    from blobctrl_b200 import ops
+    pyr_k = ops.halving_pyramid(out["scores_pyramid"][64], 8)
+    for s in (32, 16, 8):
+        assert torch.equal(out["scores_pyramid"][s], pyr_k[s]), f"cfg3 full batch pyramid@{s}"
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
