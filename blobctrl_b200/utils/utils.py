@@ -2,8 +2,10 @@
 
 Same names, keyword arguments, defaults, return shapes, dict keys and error behaviour as the
 reference functions cited below; the arithmetic runs in hand-written sm_100a CUDA kernels behind
-the C ABI of ``include/blobsplat.h`` (see ``blobctrl_b200/ops.py``).  Inputs must be CUDA tensors —
-there is no CPU path and no PyTorch fallback.
+the C ABI of ``include/blobsplat.h`` (see ``blobctrl_b200/ops.py``).  There is no CPU path and no PyTorch
+fallback: the maps are always rendered by the CUDA kernels and always live on the GPU.  ``splat_features`` takes the
+blob dict as the reference's scripts build it — host tensors (scripts/blobctrl_inference.py:101-109) — by uploading the
+few bytes of parameters to the current CUDA device first; without a CUDA device it raises.
 
 Behavioural notes (each mirrors a line of the reference):
   * pixel centres sit at integer coordinates, x = p % W, y = p // W, no half-pixel offset (utils.py:139-142);
@@ -128,6 +130,16 @@ def _viz_same_size(viz_size, h: int, w: int) -> bool:
     return viz_size is not None and (int(viz_size[0]), int(viz_size[1])) == (h, w)
 
 
+def _upload_host_blobs(xs, ys, covs, sizes, features, kwargs):
+    if not torch.cuda.is_available():
+        C.require_cuda(covs, "covs")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    up = lambda t: t.to(dev, non_blocking=True) if torch.is_tensor(t) and not t.is_cuda else t
+    if torch.is_tensor(kwargs.get("viz_colors")):
+        kwargs = dict(kwargs, viz_colors=up(kwargs["viz_colors"]))
+    return up(xs), up(ys), up(covs), up(sizes), up(features), kwargs
+
+
 def splat_features(
         xs: Tensor,
         ys: Tensor,
@@ -176,7 +188,11 @@ def splat_features(
     out_dtype = kwargs.get("out_dtype")
     composite_mode = kwargs.get("composite_mode", "auto")
     engine = kwargs.get("engine", "auto")
-    C.require_cuda(covs, "covs")
+    if not covs.is_cuda:
+        # the scripts' blob dict (blobctrl_inference.py:101-109, blobctrl_app.py:520-528) is built from numpy on the host and
+        # the result moved with .to(device) / .cpu() afterwards (:174, blobctrl_app.py:645): upload the parameters, render on
+        # the GPU, return GPU maps.  No device -> require_cuda raises: nothing is ever computed on the host.
+        xs, ys, covs, sizes, features, kwargs = _upload_host_blobs(xs, ys, covs, sizes, features, kwargs)
     h, w = _render_hw(covs, score_size, viz_size)
     m = covs.shape[1]
     select = "bg" if only_splatting_bg else ("fg" if only_splatting_fg else "all")

@@ -84,6 +84,14 @@ def test_forty_demo_ellipses_fp64_script_recipe():
         got = score.cpu().numpy()
         close_scaled(got[1], want[i], 1e-9, f"{e['demo']}[{e['idx']}] fg")
         close_scaled(got[0], 1 - want[i], 1e-9, f"{e['demo']}[{e['idx']}] bg")
+        if i < 8:
+            # the scripts' own blob dict — host tensors, as blobctrl_inference.py:101-109 builds them — through the
+            # import swap alone: uploaded, rendered on the GPU, same bits; the preview takes the host palette too
+            host = U.get_blob_dict_from_norm_gs(nm, nc, device="cpu")
+            hs = U.get_blob_score_from_blob_dict(host, score_size=(64, 64))
+            assert hs.is_cuda and torch.equal(hs, score)
+            hv = U.get_blob_vis_img_from_blob_dict(host, viz_size=(64, 64), score_size=(64, 64))
+            assert hv.is_cuda and torch.equal(hv, U.get_blob_vis_img_from_blob_dict(blob, viz_size=(64, 64), score_size=(64, 64)))
         # same ellipse with float32 tensors: 1e-5 of scale against the float64 reference
         b32 = {k: (v.float()) for k, v in blob.items()}
         got32 = U.get_blob_score_from_blob_dict(b32, score_size=(64, 64)).cpu().numpy()
@@ -273,9 +281,14 @@ def test_errors_and_no_cpu_fallback():
     U = _impl()
     syn = blob_oracle.synthetic_blobs(2, 3, seed=9, c=4)
     cpu = {k: torch.from_numpy(v) for k, v in syn.items() if k != "features"}
+    with pytest.raises(RuntimeError, match="no CPU"):       # the stage functions take device maps only
+        U.splat_features_from_scores(torch.rand(2, 4, 8, 8), torch.from_numpy(syn["features"]), 8, channels_last=False)
     with pytest.raises(RuntimeError, match="no CPU"):
-        U.splat_features(**cpu, score_size=8, return_d_score=True)
+        U.pyramid_resize(torch.rand(2, 4, 8, 8), 4)
     b = _blob(syn)
+    # the renderer takes the scripts' host-built blob dict: parameters are uploaded, maps are rendered and stay on the GPU
+    up = U.splat_features(**cpu, score_size=8, return_d_score=True)
+    assert up.is_cuda and torch.equal(up, U.splat_features(**b, score_size=8, return_d_score=True))
     with pytest.raises(RuntimeError):                       # tuple size with N*M > 1 (utils.py:157-159)
         U.splat_features(**b, score_size=(8, 8), return_d_score=True)
     with pytest.raises(TypeError):                          # interp_size missing (utils.py:291)
