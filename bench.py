@@ -353,10 +353,15 @@ def main():
     step_bytes = algorithmic_bytes(N_IMG, M_BLOBS, P, CHANNELS, 4, 4)
     dom = max(kern, key=lambda k: k["ms"])
     traffic, traffic_src = measured_traffic(dom["name"])
-    roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / peak,
+    # a step of this workload IS one launch of the dominant kernel (gpu_launches = steps): its average launch duration over the
+    # timed region is the region's CUDA-event time / steps.  The same launch bracketed by its own pair of events, in a loop
+    # of its own before the timed region, is kept beside it (events between launches cost ~2 % at this size).
+    launch_ms = total / args.steps * 1e3 if len(kern) == 1 else dom["ms"]
+    roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["alg_bytes"] / (launch_ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": dom["alg_bytes"] / (launch_ms * 1e-3) / 1e9 / peak,
             "traffic": traffic, "traffic_source": traffic_src, "kernel_source_sha16": kernel_source_sha(),
-            "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": dom["ms"],
+            "peak_source": peak_src, "alg_bytes_per_launch": dom["alg_bytes"], "avg_launch_ms": launch_ms,
+            "avg_launch_ms_bracketed": dom["ms"], "frac_bracketed": dom["alg_bytes"] / (dom["ms"] * 1e-3) / 1e9 / peak,
             "step_alg_bytes": step_bytes, "step_frac": step_bytes / (total / args.steps) / 1e9 / peak,
             "sustained": {"seconds": args.sustained_seconds, "steps": sus_calls, "ms_per_step": sus_ms,
                           "achieved": step_bytes / (sus_ms * 1e-3) / 1e9, "frac": step_bytes / (sus_ms * 1e-3) / 1e9 / peak,
