@@ -253,6 +253,42 @@ def test_full_size_properties_config5():
     close_scaled(_np(g[sl]), want["feature_grid"], 1e-5, "cfg5 grid slice")
 
 
+def _have_reference():
+    import os
+    return os.path.isdir(os.path.join(os.path.dirname(G.HERE), "baseline", "_ref", "blobctrl"))
+
+
+@pytest.mark.skipif(not _have_reference(), reason="baseline/_ref not installed (scripts/install_reference.sh)")
+def test_full_size_config5_whole_batch_against_the_installed_reference():
+    """BASELINE config 5 at full size, EVERY image: the fused float32 render against the UNMODIFIED reference
+    splat_features (baseline/_ref, blobctrl/utils/utils.py:80-241) run on this GPU in float64 on the same float32
+    inputs, 256 images at a time — 1e-5 of scale on the composed maps and on the feature grid."""
+    from baseline import ref_loader
+    R = ref_loader.load(need_pipeline=False).utils
+    U = _impl()
+    n, m, s, c = 1024, 64, 64, 320
+    syn = blob_oracle.synthetic_blobs(n, m, seed=0, c=c)
+    b = _blob(syn)
+    f = _cuda(syn["features"])
+    out = U.splat_features(**b, features=f, score_size=s, interp_size=s, ret_layout=False)
+    d, g = out["scores_pyramid"][s], out["feature_grid"]
+    worst_d = worst_g = 0.0
+    for lo in range(0, n, 256):
+        sl = slice(lo, lo + 256)
+        ref = R.splat_features(**{k: v[sl].double() for k, v in b.items()}, features=f[sl].double(), score_size=s,
+                               interp_size=s, ret_layout=False)
+        rd, rg = ref["scores_pyramid"][s], ref["feature_grid"]
+        assert rd.dtype == torch.float64 and rd.shape == d[sl].shape and rg.shape == g[sl].shape
+        worst_d = max(worst_d, (d[sl].double() - rd).abs().max().item())                       # scores live in [0, 1]
+        worst_g = max(worst_g, ((g[sl].double() - rg).abs().amax(dim=(1, 2, 3)) / rg.abs().amax(dim=(1, 2, 3))).max().item())
+        am_ours, am_ref = d[sl].argmax(1), rd.argmax(1)                                          # front-most visible blob per pixel
+        top2 = rd.topk(2, dim=1).values
+        sure = (top2[:, 0] - top2[:, 1]) > 1e-5
+        assert torch.equal(am_ours[sure], am_ref[sure])
+        del ref, rd, rg
+    assert worst_d <= 1e-5 and worst_g <= 1e-5, (worst_d, worst_g)
+
+
 def test_pipeline_conditioning_entry():
     """pipeline_blobnet.py:973-984 + :724-739: K=1, C=1024, fp16, layouts [2B,1029,64,128] / [2B,5,64,128]."""
     from blobctrl_b200.pipelines import construct_blobnet_input, prepare_blob_conditioning
@@ -600,6 +636,32 @@ def test_full_size_config3_properties():
     pyr_k = ops.halving_pyramid(out["scores_pyramid"][64], 8)
     for s in (32, 16, 8):
         assert torch.equal(out["scores_pyramid"][s], pyr_k[s]), f"cfg3 full batch pyramid@{s}"
+
+
+@pytest.mark.skipif(not _have_reference(), reason="baseline/_ref not installed (scripts/install_reference.sh)")
+def test_full_size_config3_whole_batch_against_the_installed_reference():
+    """BASELINE config 3, every image and level: bf16 maps of the one-call multi-scale render against the UNMODIFIED
+    reference on this GPU in float64 — splat_features for the 64x64 maps, its pyramid_resize for the lower levels, its
+    splat_features_from_scores per level (utils.py:80-241, 280-294, 57-77) — at 1e-2 of scale (the reference cannot run bf16)."""
+    from baseline import ref_loader
+    R = ref_loader.load(need_pipeline=False).utils
+    U = _impl()
+    n, m = 64, 32
+    syn = blob_oracle.synthetic_blobs(n, m, seed=0)
+    chans = {64: 320, 32: 640, 16: 1280, 8: 1280}
+    g = torch.Generator().manual_seed(1)
+    feats = {s: torch.randn(n, m + 1, c, generator=g).to(DEV).to(torch.bfloat16) for s, c in chans.items()}
+    b = _blob(syn)
+    out = U.splat_features_multiscale(**b, score_size=64, level_features=feats, out_dtype=torch.bfloat16)
+    rd = R.splat_features(**{k: v.double() for k, v in b.items()}, score_size=64, return_d_score=True)
+    pyr = R.pyramid_resize(rd, cutoff=8)
+    assert sorted(pyr) == [8, 16, 32, 64]
+    for s in chans:
+        err = (out["scores_pyramid"][s].double() - pyr[s]).abs().max().item()
+        assert err <= 1e-2, f"cfg3 scores@{s} vs reference: {err}"
+        want = R.splat_features_from_scores(pyr[s], feats[s].double(), s, channels_last=False)
+        err = (out["feature_grids"][s].double() - want).abs().max().item()
+        assert err <= 1e-2 * want.abs().max().item(), f"cfg3 grid@{s} vs reference: {err}"
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
@@ -959,11 +1021,6 @@ def test_residual_injection_accepts_the_pipelines_cropped_views():
         odd = res[:, :, :, 3:11]                           # not the right-most columns: falls back to a contiguous copy
         want2 = hidden.clone(); want2[..., -8:] = want2[..., -8:] + odd
         assert torch.equal(inject_residual(hidden.clone(), odd, 1.0), want2)
-
-
-def _have_reference():
-    import os
-    return os.path.isdir(os.path.join(os.path.dirname(G.HERE), "baseline", "_ref", "blobctrl"))
 
 
 @pytest.mark.skipif(not _have_reference(), reason="baseline/_ref not installed (scripts/install_reference.sh)")
