@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
+#include <string>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
 template <int MODE>
@@ -47,7 +48,34 @@ __global__ void __launch_bounds__(512) drain(unsigned char* out, int N, int C, i
   }
 }
 
-int main() {
+// drain_pattern sustained <seconds> [mode]: the cfg5c-sized store stream (mode 1 by default) back to back for that long, one line per
+// ~0.25 s — does the bare store stream hold its burst rate once the power state has ramped?  (Sample clocks beside it with nvidia-smi.)
+static int sustained(double seconds, int mode) {
+  int clk_khz, sms; CK(cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  const int N = 1024, C = 320, P = 4096;
+  const size_t bytes = (size_t)N * C * P * 2;
+  unsigned char* buf; CK(cudaMalloc(&buf, bytes));
+  const int tiles = (P + 255) / 256, groups = (C + 127) / 128, items = N * tiles * groups;
+  cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  double elapsed = 0;
+  while (elapsed < seconds) {
+    const int reps = 500;
+    CK(cudaEventRecord(a));
+    for (int i = 0; i < reps; ++i) {
+      if (mode == 0) drain<0><<<sms, 512>>>(buf, N, C, P, items, tiles, groups);
+      else drain<1><<<sms, 512>>>(buf, N, C, P, items, tiles, groups);
+    }
+    CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+    float ms; CK(cudaEventElapsedTime(&ms, a, b));
+    elapsed += ms * 1e-3;
+    printf("t = %5.2f s  mode %d: %7.1f us per 2.7 GB  %5.2f TB/s\n", elapsed, mode, ms / reps * 1e3, bytes / (ms / reps) / 1e9);
+    fflush(stdout);
+  }
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 2 && std::string(argv[1]) == "sustained") return sustained(atof(argv[2]), argc > 3 ? atoi(argv[3]) : 1);
   int clk_khz, sms; CK(cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0)); CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
   struct Shape { const char* name; int N, C, P; } shapes[] = {{"cfg3 level 32 (84 MB)", 64, 640, 1024}, {"cfg3 level 16 (42 MB)", 64, 1280, 256},
