@@ -135,7 +135,8 @@ def require_cuda(t: torch.Tensor, what: str) -> None:
 
 
 def ptr(t: Optional[torch.Tensor]):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Device address as a plain int (the declared argtypes convert it): no ctypes object per argument on the latency path."""
+    return None if t is None else t.data_ptr()
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -145,8 +146,8 @@ def stream_of(t: torch.Tensor):
     """The current CUDA stream of the tensor's device as a raw handle.  torch.cuda.current_stream() builds a Stream
     object (~8 us per call — a third of a small launch); the raw accessor is the same lookup without it."""
     if _raw_stream is not None:
-        return ctypes.c_void_p(_raw_stream(dev_of(t)))
-    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        return _raw_stream(dev_of(t)) or None
+    return torch.cuda.current_stream(t.device).cuda_stream or None
 
 
 def dev_of(t: torch.Tensor) -> int:

@@ -218,7 +218,9 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
         raise C.BlobSplatUnsupported("blobsplat: unsupported: fused render takes float32 blob parameters")
     if out_dtype is None:
         out_dtype = features.dtype
-    f = features.to(device=covs_c.device, dtype=out_dtype).contiguous()     # utils.py:69
+    f = features
+    if f.dtype != out_dtype or f.device != covs_c.device or not f.is_contiguous():
+        f = features.to(device=covs_c.device, dtype=out_dtype).contiguous()     # utils.py:69
     if f.ndim != 3 or f.shape[0] != n or f.shape[1] != m + 1:
         raise RuntimeError(f"features must be [N, M+1, C] = [{n}, {m + 1}, C], got {tuple(f.shape)}")
     c = f.shape[2]

@@ -170,7 +170,9 @@ def splat_features(
     Extra keyword-only extensions (absent from the reference): ``out_dtype``, ``composite_mode``
     ('auto' | 'lane_pixel' | 'warp_scan'), ``engine`` ('auto' | 'fma' | 'tensor'), ``cuda_graph`` (bool, default False:
     replay a captured CUDA graph of this exact call — the latency path for N = 1; the returned tensors are then the
-    graph's static buffers, see blobctrl_b200/graphs.py).
+    graph's static buffers, see blobctrl_b200/graphs.py), ``check_singular`` (bool, default False: raise like the reference's
+    ``torch.linalg.solve`` (utils.py:143) when a covariance has a zero or non-finite determinant — one device-to-host
+    synchronisation per call, which is why it is opt-in; without it such a blob yields non-finite maps).
     """
     if kwargs.get("cuda_graph"):
         # opt-in: replay a captured graph of this exact call (blobctrl_b200/graphs.py); outputs are static buffers
@@ -193,6 +195,11 @@ def splat_features(
         # the result moved with .to(device) / .cpu() afterwards (:174, blobctrl_app.py:645): upload the parameters, render on
         # the GPU, return GPU maps.  No device -> require_cuda raises: nothing is ever computed on the host.
         xs, ys, covs, sizes, features, kwargs = _upload_host_blobs(xs, ys, covs, sizes, features, kwargs)
+    if kwargs.get("check_singular"):
+        c64 = covs.double()
+        det = c64[..., 0, 0] * c64[..., 1, 1] - c64[..., 0, 1] * c64[..., 1, 0]
+        if not bool(((det != 0) & torch.isfinite(det)).all()):          # the reference's error text (torch.linalg.solve)
+            raise torch.linalg.LinAlgError("torch.linalg.solve: The solver failed because the input matrix is singular.")
     h, w = _render_hw(covs, score_size, viz_size)
     m = covs.shape[1]
     select = "bg" if only_splatting_bg else ("fg" if only_splatting_fg else "all")

@@ -333,6 +333,11 @@ def test_errors_and_no_cpu_fallback():
         U.splat_features(**b, score_size=8, interp_size=16, features=_cuda(syn["features"]))
     with pytest.raises(RuntimeError):                       # feature rows != channels
         U.splat_features(**b, score_size=8, interp_size=8, features=_cuda(syn["features"])[:, :2])
+    sing = {k: v.clone() for k, v in b.items()}
+    sing["covs"][1, 2] = torch.tensor([[0.01, 0.02], [0.02, 0.04]], device=DEV)              # rank 1
+    with pytest.raises(RuntimeError, match="singular"):      # the reference's torch.linalg.solve raises (utils.py:143); opt-in here
+        U.splat_features(**sing, score_size=8, return_d_score=True, check_singular=True)
+    assert U.splat_features(**b, score_size=8, return_d_score=True, check_singular=True).shape == (2, 4, 8, 8)
     from blobctrl_b200 import _capi
     with pytest.raises(_capi.BlobSplatError):               # warp-scan limit
         big = blob_oracle.synthetic_blobs(1, 300, seed=1)
