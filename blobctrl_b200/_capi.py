@@ -16,7 +16,7 @@ F32, F64, BF16, F16 = 0, 1, 2, 3
 SELECT_ALL, SELECT_FG, SELECT_BG = 0, 1, 2
 COMPOSITE_AUTO, COMPOSITE_LANE_PIXEL, COMPOSITE_WARP_SCAN = 0, 1, 2
 ENGINE_AUTO, ENGINE_FMA, ENGINE_TENSOR, ENGINE_TMA = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -55,6 +55,7 @@ SIGNATURES = {
     "blobsplat_scores": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P],
     "blobsplat_scores_ellipse": [_P, _P, ctypes.c_float, ctypes.c_float, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P],
     "blobsplat_preview": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
+    "blobsplat_preview_u8": [_P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "blobsplat_composite": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_resize_bilinear": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_pyramid": [_P, ctypes.POINTER(_P), _I, _I, _I, _I, _I, _P],

@@ -48,7 +48,7 @@ int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, i
                                cudaStream_t);
 int residual_inject_dispatch(void*, const void*, const float*, float, int, int, int, int, int, int, int, cudaStream_t);
 int preview_dispatch(const void*, const void*, const void*, const float*, int, const void*, int, int, int, int, int, void*, void*,
-                     cudaStream_t);
+                     unsigned char*, cudaStream_t);
 int conv_in_weights_dispatch(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int conv_in_hoisted_dispatch(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int, int, int,
                              int, int, int, cudaStream_t);
@@ -149,7 +149,22 @@ int blobsplat_preview(const void* xs, const void* ys, const void* covs, const fl
   BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
   DeviceGuard g(device);
   if (g.status) return g.status;
-  return preview_dispatch(xs, ys, covs, sizes, param_dtype, colors, colors_per_image, N, M, H, W, image, composed, (cudaStream_t)stream);
+  return preview_dispatch(xs, ys, covs, sizes, param_dtype, colors, colors_per_image, N, M, H, W, image, composed, nullptr,
+                          (cudaStream_t)stream);
+}
+
+int blobsplat_preview_u8(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype, const void* colors,
+                         int colors_per_image, int N, int M, int H, int W, unsigned char* image_hwc, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1, "bad shape N=%d M=%d H=%d W=%d", N, M, H, W);
+  BS_CHECK_ARG(M <= kMaxBlobs && N <= 65535 && (long long)H * W < (1ll << 31), "shape too large");
+  BS_CHECK_ARG(param_dtype == BLOBSPLAT_F32 || param_dtype == BLOBSPLAT_F64, "preview renders float32 or float64 (got %d)", param_dtype);
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(image_hwc && colors, "NULL image / colour pointer");
+  BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return preview_dispatch(xs, ys, covs, sizes, param_dtype, colors, colors_per_image, N, M, H, W, nullptr, nullptr, image_hwc,
+                          (cudaStream_t)stream);
 }
 
 int blobsplat_composite(const void* scores_in, void* composed, int N, int K, int H, int W, int dtype, int device,

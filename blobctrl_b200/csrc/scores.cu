@@ -264,7 +264,7 @@ template <typename PT, int V>
 __global__ void __launch_bounds__(kScoreThreads)
 preview_kernel(const PT* __restrict__ xs, const PT* __restrict__ ys, const PT* __restrict__ covs,
                const float* __restrict__ sizes, const PT* __restrict__ colors, int colors_per_image, int M, int H, int W,
-               PT* __restrict__ image, PT* __restrict__ composed) {
+               PT* __restrict__ image, PT* __restrict__ composed, unsigned char* __restrict__ image_u8) {
   constexpr bool kF64 = sizeof(PT) == 8;
   using Coef = typename std::conditional<kF64, BlobCoefD, BlobCoef>::type;
   __shared__ Coef coef[kBlobChunk];
@@ -330,12 +330,31 @@ preview_kernel(const PT* __restrict__ xs, const PT* __restrict__ ys, const PT* _
   }
   if (!active) return;
   if (cbase) VecStore<PT, V>::st(cbase, T);
+  unsigned char px8[3 * V];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     PT v[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = rgb[ch][j] + T[j] * cb[ch];          // background: alpha 1 * transmittance
-    VecStore<PT, V>::st(image + ((size_t)n * 3 + ch) * P + pix, v);
+    for (int j = 0; j < V; ++j) {
+      v[j] = rgb[ch][j] + T[j] * cb[ch];                                    // background: alpha 1 * transmittance
+      // the app's conversion (blobctrl_app.py:645-646): (img * 255).astype(np.uint8) = truncation of the product in PT
+      px8[3 * j + ch] = (unsigned char)(int)(v[j] * (PT)255);
+    }
+    if (image) VecStore<PT, V>::st(image + ((size_t)n * 3 + ch) * P + pix, v);
+  }
+  if (image_u8) {                                                           // [N, H, W, 3]: this thread's 3 V bytes are contiguous
+    unsigned char* const o = image_u8 + ((size_t)n * P + pix) * 3;
+    if constexpr ((3 * V) % 4 == 0) {
+#pragma unroll
+      for (int w = 0; w < 3 * V / 4; ++w)
+        reinterpret_cast<unsigned int*>(o)[w] = px8[4 * w] | (px8[4 * w + 1] << 8) | (px8[4 * w + 2] << 16) | ((unsigned)px8[4 * w + 3] << 24);
+    } else if constexpr ((3 * V) % 2 == 0) {
+#pragma unroll
+      for (int w = 0; w < 3 * V / 2; ++w) reinterpret_cast<unsigned short*>(o)[w] = (unsigned short)(px8[2 * w] | (px8[2 * w + 1] << 8));
+    } else {
+#pragma unroll
+      for (int w = 0; w < 3 * V; ++w) o[w] = px8[w];
+    }
   }
 }
 
@@ -459,26 +478,27 @@ int scores_ellipse_dispatch(const float* ell, const float* sizes, float img_w, f
 }
 
 int preview_dispatch(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype, const void* colors,
-                     int colors_per_image, int N, int M, int H, int W, void* image, void* composed, cudaStream_t st) {
+                     int colors_per_image, int N, int M, int H, int W, void* image, void* composed, unsigned char* image_u8,
+                     cudaStream_t st) {
   const int P = H * W;
   if (param_dtype == BLOBSPLAT_F64) {
-    const bool vec = (W % 2 == 0) && aligned_to(image, 16) && aligned_to(composed, 16);
+    const bool vec = (W % 2 == 0) && aligned_to(image, 16) && aligned_to(composed, 16) && aligned_to(image_u8, 2);
     dim3 grid((unsigned)((P / (vec ? 2 : 1) + kScoreThreads - 1) / kScoreThreads), (unsigned)N);
     if (vec)
       preview_kernel<double, 2><<<grid, kScoreThreads, 0, st>>>((const double*)xs, (const double*)ys, (const double*)covs, sizes,
-                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed);
+                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed, image_u8);
     else
       preview_kernel<double, 1><<<grid, kScoreThreads, 0, st>>>((const double*)xs, (const double*)ys, (const double*)covs, sizes,
-                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed);
+                                                                (const double*)colors, colors_per_image, M, H, W, (double*)image, (double*)composed, image_u8);
   } else if (param_dtype == BLOBSPLAT_F32) {
-    const bool vec = (W % 4 == 0) && aligned_to(image, 16) && aligned_to(composed, 16);
+    const bool vec = (W % 4 == 0) && aligned_to(image, 16) && aligned_to(composed, 16) && aligned_to(image_u8, 4);
     dim3 grid((unsigned)((P / (vec ? 4 : 1) + kScoreThreads - 1) / kScoreThreads), (unsigned)N);
     if (vec)
       preview_kernel<float, 4><<<grid, kScoreThreads, 0, st>>>((const float*)xs, (const float*)ys, (const float*)covs, sizes,
-                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed);
+                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed, image_u8);
     else
       preview_kernel<float, 1><<<grid, kScoreThreads, 0, st>>>((const float*)xs, (const float*)ys, (const float*)covs, sizes,
-                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed);
+                                                               (const float*)colors, colors_per_image, M, H, W, (float*)image, (float*)composed, image_u8);
   } else {
     BS_UNSUPPORTED("preview renders float32 or float64 (got %d)", param_dtype);
   }

@@ -326,6 +326,27 @@ def render_preview(xs, ys, covs, sizes, colors: torch.Tensor, height: int, width
     return image, composed
 
 
+def render_preview_u8(xs, ys, covs, sizes, colors: torch.Tensor, height: int, width: int) -> torch.Tensor:
+    """The preview as the 8-bit picture the UI shows (blobsplat_preview_u8): [N, H, W, 3] uint8 =
+    (image.permute(0, 2, 3, 1) * 255) truncated like numpy's astype(np.uint8) (scripts/blobctrl_app.py:645-646), straight
+    from the render launch — a quarter (float32) or an eighth (float64) of the bytes to bring back to the host."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    dt, dev = covs_c.dtype, covs_c.device
+    col = colors.to(device=dev, dtype=dt)
+    if col.ndim == 2:
+        col, per_image = col[: m + 1].contiguous(), 0
+    elif col.ndim == 3 and col.shape[0] == n:
+        col, per_image = col[:, : m + 1].contiguous(), 1
+    else:
+        raise RuntimeError(f"colors must be [K, 3] or [N, K, 3], got {tuple(colors.shape)}")
+    if col.shape[-2] < m + 1 or col.shape[-1] != 3:
+        raise RuntimeError(f"colors must hold {m + 1} RGB rows, got {tuple(colors.shape)}")
+    image = torch.empty((n, height, width, 3), dtype=torch.uint8, device=dev)
+    C.check(C.lib().blobsplat_preview_u8(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.dtype_code(dt), C.ptr(col), per_image,
+                                         n, m, height, width, C.ptr(image), C.dev_of(covs_c), C.stream_of(covs_c)))
+    return image
+
+
 def conv_in_weights(weight: torch.Tensor, features: torch.Tensor, latent_channels: int = 4) -> torch.Tensor:
     """blobsplat_conv_in_weights: per-sample effective 3x3 kernels of the conditioning planes of BlobNet's conv_in.
     weight [O, lc+1+C, 3, 3], features [B, K, C] -> weff [B, O, 1+K, 12] float32 (9 taps padded to 12)."""

@@ -413,6 +413,21 @@ def get_blob_vis_img_from_blob_dict(blob, viz_size=64, score_size=64):
                           only_vis=True)["feature_img"]
 
 
+def get_blob_vis_u8_from_blob_dict(blob, viz_size=64):
+    """scripts/blobctrl_app.py:637-648 up to ``Image.fromarray``: the preview of image 0 as a host uint8 array [H, W, 3]
+    (``Image.fromarray(get_blob_vis_u8_from_blob_dict(blob, viz_size))`` is the app's ``blob_vis_img``).  One launch
+    renders, permutes and converts; the device-to-host copy moves 3 bytes per pixel."""
+    covs = blob["covs"]
+    if not covs.is_cuda:
+        xs, ys, covs, sizes, _, _ = _upload_host_blobs(blob["xs"], blob["ys"], covs, blob["sizes"], None, {})
+    else:
+        xs, ys, sizes = blob["xs"], blob["ys"], blob["sizes"]
+    h, w = (viz_size, viz_size) if isinstance(viz_size, int) else (int(viz_size[0]), int(viz_size[1]))
+    if isinstance(viz_size, tuple) and (covs.shape[0] != 1 or covs.shape[1] != 1):
+        raise RuntimeError(f"shape '[1, 1, {h}, {w}]' is invalid for input of size {covs.shape[0] * covs.shape[1] * h * w}")
+    return ops.render_preview_u8(xs, ys, covs, sizes, BLOB_VIS_COLORS, h, w)[0].cpu().numpy()
+
+
 # --------------------------------------------------------------------------------------------------
 # overlay helpers (host side, OpenCV) — same names and behaviour as utils.py:393-456; imported by the scripts
 # (scripts/blobctrl_app.py:26)

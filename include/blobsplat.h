@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BLOBSPLAT_ABI_VERSION 2
+#define BLOBSPLAT_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define BLOBSPLAT_API __attribute__((visibility("default")))
@@ -135,6 +135,18 @@ BLOBSPLAT_API int blobsplat_scores_ellipse(const float* ellipses, const float* s
 BLOBSPLAT_API int blobsplat_preview(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype,
                       const void* colors, int colors_per_image, int N, int M, int H, int W,
                       void* image, void* composed, int device, void* stream);
+
+/*
+ * (1d) preview as the 8-bit picture the UI shows.  Replaces the whole of get_blob_vis_img_from_blob_dict up to
+ *      Image.fromarray (scripts/blobctrl_app.py:637-648): the preview above, then
+ *      blob_vis[0].permute(1, 2, 0).contiguous().cpu().numpy(); (img * 255).astype(np.uint8)
+ *      — the permute and the conversion happen in the render launch, and the device-to-host copy moves 3 bytes per
+ *      pixel instead of 12 (float32) or 24 (float64).
+ *   image_hwc [N, H, W, 3] uint8 = truncation of value * 255 computed in param_dtype (numpy's astype).
+ */
+BLOBSPLAT_API int blobsplat_preview_u8(const void* xs, const void* ys, const void* covs, const float* sizes, int param_dtype,
+                         const void* colors, int colors_per_image, int N, int M, int H, int W,
+                         unsigned char* image_hwc, int device, void* stream);
 
 /*
  * (1b) composite only.  Replaces utils.py:179-181 / :205-206 applied to caller-modified raw scores

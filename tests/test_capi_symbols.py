@@ -25,7 +25,7 @@ def test_header_declares_the_expected_entry_points():
     assert set(d) == {"blobsplat_abi_version", "blobsplat_get_caps", "blobsplat_last_error", "blobsplat_scores",
                       "blobsplat_scores_ellipse", "blobsplat_composite", "blobsplat_resize_bilinear", "blobsplat_pyramid",
                       "blobsplat_feature_splat", "blobsplat_feature_splat_levels", "blobsplat_conditioning_fill", "blobsplat_residual_inject", "blobsplat_render", "blobsplat_render_multiscale",
-                      "blobsplat_preview", "blobsplat_conv_in_weights", "blobsplat_conv_in_hoisted"}
+                      "blobsplat_preview", "blobsplat_preview_u8", "blobsplat_conv_in_weights", "blobsplat_conv_in_hoisted"}
 
 
 def test_library_exports_every_declared_symbol():
@@ -52,7 +52,7 @@ def test_binding_matches_header_arity_and_abi_version():
 def test_caps_and_argument_validation_without_a_gpu():
     from blobctrl_b200 import _capi
     c = _capi.caps()
-    assert c.abi_version == _capi.ABI_VERSION == 2 and c.sm_arch == 100 and c.max_blobs >= 65536
+    assert c.abi_version == _capi.ABI_VERSION == 3 and c.sm_arch == 100 and c.max_blobs >= 65536
     L = _capi.lib()
     # invalid arguments are rejected before any CUDA call
     assert L.blobsplat_scores(None, None, None, None, 0, 1, 1, 0, 8, 0, None, 0, None, 0, 0, -1, None) == -1
@@ -71,6 +71,8 @@ def test_caps_and_argument_validation_without_a_gpu():
     assert L.blobsplat_composite(None, None, 0, 3, 4, 4, 0, -1, None) == 0
     assert L.blobsplat_preview(None, None, None, None, 0, None, 0, 0, 1, 8, 8, None, None, -1, None) == 0
     assert L.blobsplat_preview(None, None, None, None, 2, None, 0, 1, 1, 8, 8, None, None, -1, None) == -1
+    assert L.blobsplat_preview_u8(None, None, None, None, 0, None, 0, 0, 1, 8, 8, None, -1, None) == 0
+    assert L.blobsplat_preview_u8(None, None, None, None, 0, None, 0, 1, 1, 8, 8, None, -1, None) == -1     # NULL image
     assert L.blobsplat_conv_in_weights(None, None, None, 1, 8, 30, 4, 20, 1, 0, -1, None) == -1      # Cin != lc + 1 + C
     assert "input planes" in _capi.last_error()
     assert L.blobsplat_conv_in_hoisted(None, None, None, None, None, None, 0, 8, 25, 4, 2, 4, 4, 2, 0, -1, None) == 0

@@ -849,6 +849,14 @@ def test_preview_one_launch_vs_oracle_and_the_three_launch_path(dtype, rel):
         assert img.shape == (n, 3, h, w) and img.dtype == dtype
         close_scaled(_np(img), want, rel, f"preview {n}x{m}x{h}x{w}")
         close_scaled(_np(comp), np.moveaxis(d, -1, 1), rel, "preview composed")
+        # the 8-bit picture (blobsplat_preview_u8): exactly the app's conversion of the float image (blobctrl_app.py:645-646),
+        # permute and truncation done in the launch; within one count of the float64 oracle's picture
+        u8 = ops.render_preview_u8(b["xs"], b["ys"], b["covs"], b["sizes"], _cuda(colors).to(dtype), h, w)
+        assert u8.shape == (n, h, w, 3) and u8.dtype == torch.uint8
+        app = (img.permute(0, 2, 3, 1).contiguous().cpu().numpy() * 255).astype(np.uint8)
+        assert np.array_equal(u8.cpu().numpy(), app), f"u8 preview {n}x{m}x{h}x{w}"
+        ref8 = (np.moveaxis(want, 1, -1) * 255).astype(np.uint8)
+        assert np.abs(u8.cpu().numpy().astype(np.int16) - ref8.astype(np.int16)).max() <= 1
     # through the reference-signature API: the UI call (blobctrl_app.py:637-646) takes the one-launch path
     blob = blob_oracle.blob_from_ellipse(G.ellipses()[12]["ellipse"], 512, 512)
     bb = {k: _cuda(v).to(dtype) if k != "sizes" else _cuda(v) for k, v in blob.items()}
@@ -856,6 +864,13 @@ def test_preview_one_launch_vs_oracle_and_the_three_launch_path(dtype, rel):
     d2, _ = ops.render_scores(bb["xs"], bb["ys"], bb["covs"], bb["sizes"], 128, 128)
     three = ops.feature_splat(d2, U.BLOB_VIS_COLORS[:2][None].to(DEV).to(dtype), engine="fma")
     assert got.dtype == dtype and (got - three).abs().max().item() <= (1e-6 if dtype == torch.float32 else 1e-14)
+    # ... and as the picture itself, from device and from host-built dicts
+    pic = U.get_blob_vis_u8_from_blob_dict(bb, viz_size=(128, 128))
+    assert pic.shape == (128, 128, 3) and pic.dtype == np.uint8
+    assert np.array_equal(pic, (got[0].permute(1, 2, 0).contiguous().cpu().numpy() * 255).astype(np.uint8))
+    host = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in blob.items()}
+    if dtype == torch.float64:
+        assert np.array_equal(U.get_blob_vis_u8_from_blob_dict(host, viz_size=(128, 128)), pic)
 
 
 def test_graphed_preview_back_to_back_without_sync():
