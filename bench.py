@@ -601,11 +601,23 @@ def variants(B, ops, dev, peak):
     pr = preview_renderer((512, 512), dev)
     hx, hy, hc = hb1["xs"].numpy(), hb1["ys"].numpy(), hb1["covs"].numpy()
     lat["cfg1_viz_512"]["graph_host_params_us"] = 1e3 * timed(lambda: pr(hx, hy, hc), reps=100)
+    # the UI's whole preview step, synchronous, host to host (blobctrl_app.py:637-648 up to Image.fromarray): host parameters
+    # in, host uint8 picture out — one graph replay (H2D of 28 bytes, preview launch writing bytes, pinned D2H of 786 KB)
+    prp = preview_renderer((512, 512), dev, picture=True)
+    for _ in range(5):
+        prp.render_picture(hx, hy, hc)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        prp.render_picture(hx, hy, hc)
+    lat["cfg1_viz_512"]["picture_host_to_host_us"] = (time.perf_counter() - t0) / 200 * 1e6
     if REF is not None:
         torch.set_num_threads(os.cpu_count() or 1)
         c64 = {k: (v.double() if k != "sizes" else v) for k, v in hb1.items()}            # the scripts feed float64
         kwv_cpu = dict(kwv, viz_colors=REF.BLOB_VIS_COLORS, viz_score_fn=REF.viz_score_fn)
         lat["cfg1_viz_512"]["reference_cpu_f64_us"] = cpu_us(lambda: REF.splat_features(**c64, **kwv_cpu))
+        import numpy as _np
+        lat["cfg1_viz_512"]["reference_cpu_f64_picture_us"] = cpu_us(
+            lambda: (REF.splat_features(**c64, **kwv_cpu)["feature_img"][0].permute(1, 2, 0).contiguous().cpu().numpy() * 255).astype(_np.uint8))
         lat["cfg1_dscore_512"]["reference_cpu_f64_us"] = cpu_us(lambda: REF.splat_features(**c64, **kwd))
         lat["cfg2"]["reference_cpu_f32_us"] = cpu_us(lambda: REF.splat_features(**hb, features=hf, score_size=64, interp_size=64,
                                                                                  ret_layout=False))

@@ -23,8 +23,13 @@ class GraphedBlobRenderer:
     call, or with a fixed colour table (``viz_colors``: the UI preview).  float32 parameters and maps."""
 
     def __init__(self, n: int, m: int, size: Tuple[int, int], channels: Optional[int] = None,
-                 viz_colors: Optional[torch.Tensor] = None, device="cuda"):
+                 viz_colors: Optional[torch.Tensor] = None, device="cuda", picture: bool = False):
         self.n, self.m, (self.h, self.w) = n, m, size
+        # picture: the preview leaves the launch as the 8-bit [N, H, W, 3] image the UI shows (blobsplat_preview_u8) and the
+        # graph ends with its copy into pinned host memory — one replay is parameters in, picture out (render_picture)
+        self.picture = bool(picture) and viz_colors is not None
+        self.pic = None
+        self.pic_host = torch.empty((n, size[0], size[1], 3), dtype=torch.uint8).pin_memory() if self.picture else None
         dev = torch.device(device)
         f32 = dict(dtype=torch.float32, device=dev)
         # one flat parameter block (xs | ys | covs | sizes) so a call is ONE host->device copy + one graph replay
@@ -59,6 +64,11 @@ class GraphedBlobRenderer:
         with torch.cuda.stream(self.stream):
             c = self.feats.shape[-1] if self.feats is not None else 0
             self.grid = None
+            if self.picture:
+                self.scores = None
+                self.pic = ops.render_preview_u8(self.xs, self.ys, self.covs, self.sizes, self.colors, self.h, self.w)
+                self.pic_host.copy_(self.pic, non_blocking=True)
+                return
             if self.colors is not None:      # the UI preview: stages 1+2 + colour splat in one launch (blobsplat_preview)
                 self.grid, self.scores = ops.render_preview(self.xs, self.ys, self.covs, self.sizes, self.colors, self.h, self.w,
                                                             want_composed=True)
@@ -98,10 +108,20 @@ class GraphedBlobRenderer:
                 self.feats.copy_(features, non_blocking=True)
             self.graph.replay()
         cur.wait_stream(self.stream)
-        return self.scores, self.grid
+        return (None, self.pic) if self.picture else (self.scores, self.grid)
+
+    def render_picture(self, xs, ys, covs, sizes=None):
+        """The UI's whole preview step (scripts/blobctrl_app.py:637-648 up to Image.fromarray), synchronous: host parameters
+        in, host uint8 picture [H, W, 3] of image 0 out (a view of the renderer's pinned buffer, rewritten by the next call)."""
+        if not self.picture:
+            raise RuntimeError("construct the renderer with picture=True (and viz_colors)")
+        self(xs, ys, covs, sizes)
+        self.stream.synchronize()
+        return self.pic_host[0].numpy()
 
 
-def preview_renderer(viz_size=(512, 512), device="cuda") -> GraphedBlobRenderer:
+def preview_renderer(viz_size=(512, 512), device="cuda", picture: bool = False) -> GraphedBlobRenderer:
     """The UI preview of scripts/blobctrl_app.py:637-646 (one image, one blob, BLOB_VIS_COLORS) as a graph:
-    ``scores, img = r(xs, ys, covs)`` -> img [1, 3, H, W] in [0, 1]."""
-    return GraphedBlobRenderer(1, 1, viz_size, viz_colors=BLOB_VIS_COLORS, device=device)
+    ``scores, img = r(xs, ys, covs)`` -> img [1, 3, H, W] in [0, 1]; with ``picture=True``
+    ``r.render_picture(xs, ys, covs)`` -> the host uint8 [H, W, 3] array ``Image.fromarray`` takes (:647-648)."""
+    return GraphedBlobRenderer(1, 1, viz_size, viz_colors=BLOB_VIS_COLORS, device=device, picture=picture)

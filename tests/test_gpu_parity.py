@@ -873,6 +873,21 @@ def test_preview_one_launch_vs_oracle_and_the_three_launch_path(dtype, rel):
         assert np.array_equal(U.get_blob_vis_u8_from_blob_dict(host, viz_size=(128, 128)), pic)
 
 
+def test_graphed_preview_picture_host_to_host():
+    """The UI's preview step as one graph replay: host parameters in, host uint8 picture out (blobctrl_app.py:637-648);
+    equal to the app's conversion of the eager float32 preview, call after call."""
+    from blobctrl_b200.preview import preview_renderer
+    U = _impl()
+    r = preview_renderer((96, 96), DEV, picture=True)
+    for i in (1, 12, 30, 5, 20):
+        b = blob_oracle.blob_from_ellipse(G.ellipses()[i]["ellipse"], 512, 512)
+        pic = r.render_picture(b["xs"], b["ys"], b["covs"]).copy()
+        b32 = {k: _cuda(v).float() for k, v in b.items()}
+        img = U.get_blob_vis_img_from_blob_dict(b32, viz_size=(96, 96))
+        assert pic.shape == (96, 96, 3) and pic.dtype == np.uint8
+        assert np.array_equal(pic, (img[0].permute(1, 2, 0).contiguous().cpu().numpy() * 255).astype(np.uint8)), i
+
+
 def test_graphed_preview_back_to_back_without_sync():
     """consecutive GraphedBlobRenderer calls with no synchronisation between them must each render their own
     parameters (the pinned staging block is double-buffered behind an event)."""
