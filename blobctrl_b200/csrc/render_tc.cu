@@ -65,3 +65,11 @@ int render_tc_dispatch(const float* xs, const float* ys, const float* covs, cons
 }
 
 }  // namespace blobsplat
+
+#if BS_TIMING
+// debug builds only: the stamps of the kernels instantiated in THIS translation unit (renders from blob parameters;
+// g_tc_timing is per translation unit, splat_tc.cu exports its own as blobsplat_debug_timing)
+extern "C" __attribute__((visibility("default"))) int blobsplat_debug_timing_render(unsigned long long* out16) {
+  return (int)cudaMemcpyFromSymbol(out16, ::g_tc_timing, sizeof(unsigned long long) * 16);
+}
+#endif

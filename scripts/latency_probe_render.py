@@ -24,7 +24,12 @@ for (n, m, c, dt, code) in ((1, 16, 320, torch.float32, 0), (1, 16, 64, torch.fl
     for _ in range(50): call()
     e.record(); torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 16)()
-    L.blobsplat_debug_timing(buf)
+    L.blobsplat_debug_timing_render(buf)
     t0 = buf[0]
-    print(f"N={n} M={m} C={c} {dt}: {a.elapsed_time(e) / 50 * 1e3:.1f} us per back-to-back launch; CTA 0 (clock64 / 1900):")
+    print(f"N={n} M={m} C={c} {dt}: {a.elapsed_time(e) / 50 * 1e3:.1f} us per back-to-back launch; CTA 0 (clock64 / 1900), last of the back-to-back "
+          f"launches (its head overlaps the previous launch's tail: programmatic dependent launch):")
     print("   " + ", ".join(f"{nm} {(buf[i] - t0) / 1900:.2f}" for i, nm in enumerate(names)))
+    torch.cuda.synchronize(); call(); torch.cuda.synchronize()
+    L.blobsplat_debug_timing_render(buf)
+    t0 = buf[0]
+    print("   alone (idle GPU before the launch): " + ", ".join(f"{nm} {(buf[i] - t0) / 1900:.2f}" for i, nm in enumerate(names)))
