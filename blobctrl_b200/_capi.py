@@ -16,7 +16,7 @@ F32, F64, BF16, F16 = 0, 1, 2, 3
 SELECT_ALL, SELECT_FG, SELECT_BG = 0, 1, 2
 COMPOSITE_AUTO, COMPOSITE_LANE_PIXEL, COMPOSITE_WARP_SCAN = 0, 1, 2
 ENGINE_AUTO, ENGINE_FMA, ENGINE_TENSOR, ENGINE_TMA = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _DTYPES = {torch.float32: F32, torch.float64: F64, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -66,6 +66,7 @@ SIGNATURES = {
     "blobsplat_conv_in_weights": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_conv_in_hoisted": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "blobsplat_render": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "blobsplat_render_small": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "blobsplat_render_multiscale": [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P],
 }
 
@@ -120,6 +121,12 @@ def check(status: int) -> None:
     if status == -2:
         raise BlobSplatUnsupported(f"blobsplat: unsupported: {msg}")
     raise BlobSplatCudaError(f"blobsplat: CUDA failure (status {status}): {msg}")
+
+
+def f32_exact() -> bool:
+    """BLOBSPLAT_F32_EXACT=1 (read per call, like the library does): float32 stage 3 stays on the FMA engine."""
+    e = os.environ.get("BLOBSPLAT_F32_EXACT")
+    return bool(e) and e[0] == "1"
 
 
 def dtype_code(dt: torch.dtype) -> int:

@@ -49,6 +49,9 @@ int conditioning_fill_dispatch(const void*, const void*, void*, int, int, int, i
 int residual_inject_dispatch(void*, const void*, const float*, float, int, int, int, int, int, int, int, cudaStream_t);
 int preview_dispatch(const void*, const void*, const void*, const float*, int, const void*, int, int, int, int, int, void*, void*,
                      unsigned char*, cudaStream_t);
+bool render_small_supported(int K);
+int render_small_dispatch(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, float*, float*,
+                          cudaStream_t);
 int conv_in_weights_dispatch(const void*, const void*, float*, int, int, int, int, int, int, int, cudaStream_t);
 int conv_in_hoisted_dispatch(const void*, const void*, const void*, const void*, const float*, void*, int, int, int, int, int, int,
                              int, int, int, cudaStream_t);
@@ -367,6 +370,19 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
   if (g.status) return g.status;
   return render_tc_dispatch(xs, ys, covs, sizes, features, feat_dtype, N, M, H, W, C, composed, grid, out_dtype,
                             (cudaStream_t)stream);
+}
+
+int blobsplat_render_small(const float* xs, const float* ys, const float* covs, const float* sizes, const float* features,
+                           int N, int M, int H, int W, int C, float* composed, float* grid, int device, void* stream) {
+  BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1 && C >= 1, "bad shape N=%d M=%d H=%d W=%d C=%d", N, M, H, W, C);
+  BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535 && (C + 31) / 32 <= 65535, "shape too large");
+  if (N == 0) return BLOBSPLAT_OK;
+  BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
+  BS_CHECK_ARG(features && grid, "NULL pointer");
+  if (!render_small_supported(M + 1)) BS_UNSUPPORTED("latency render: K = %d planes (the pixel's weights live in registers: K <= 33)", M + 1);
+  DeviceGuard g(device);
+  if (g.status) return g.status;
+  return render_small_dispatch(xs, ys, covs, sizes, features, N, M, H, W, C, composed, grid, (cudaStream_t)stream);
 }
 
 #ifndef BS_FUSED_PYRAMID_LEVELS

@@ -233,6 +233,38 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
     return composed, grid
 
 
+SMALL_RENDER_MAX_K = 33            # planes whose per-pixel weights fit in registers (render_small.cu)
+SMALL_RENDER_MAX_WORK = 3 << 23    # P * K * C multiply-adds of ONE image (25 M) up to which the latency kernel is the faster one:
+                                   # 8-10 us against 10-14 us at 8-22 M, 14.5 against 10-12 us at 43 M (graph replays, B200)
+
+
+def small_render_applies(n: int, m: int, height: int, width: int, c: int) -> bool:
+    """The one-image latency rule: a single float32 image whose stage 3 is a few microseconds of FP32 work (BASELINE config 2
+    is 22 M multiply-adds).  Batches never take it, so an image's bits do not depend on the size of the batch it is in —
+    a lone image is simply rendered with full-fp32 products instead of the split-precision tensor path (both within 1e-6)."""
+    return n == 1 and m + 1 <= SMALL_RENDER_MAX_K and height * width * (m + 1) * c <= SMALL_RENDER_MAX_WORK
+
+
+def render_small(xs, ys, covs, sizes, features: torch.Tensor, height: int, width: int, want_composed: bool = True):
+    """Stages 1+2+3 in one CUDA-core launch (blobsplat_render_small): the latency kernel for single small float32 renders.
+    Returns (composed | None, grid).  Raises BlobSplatUnsupported outside its envelope (float32, K <= 33)."""
+    xs, ys, covs_c, sizes, n, m = canonical_blobs(xs, ys, covs, sizes)
+    if covs_c.dtype != torch.float32 or features.dtype != torch.float32:
+        raise C.BlobSplatUnsupported("blobsplat: unsupported: the latency render takes float32 parameters and features")
+    f = features
+    if f.device != covs_c.device or not f.is_contiguous():
+        f = features.to(device=covs_c.device).contiguous()
+    if f.ndim != 3 or f.shape[0] != n or f.shape[1] != m + 1:
+        raise RuntimeError(f"features must be [N, M+1, C] = [{n}, {m + 1}, C], got {tuple(f.shape)}")
+    c = f.shape[2]
+    dev = covs_c.device
+    composed = C.new_output((n, m + 1, height, width), torch.float32, dev) if want_composed else None
+    grid = C.new_output((n, c, height, width), torch.float32, dev)
+    C.check(C.lib().blobsplat_render_small(C.ptr(xs), C.ptr(ys), C.ptr(covs_c), C.ptr(sizes), C.ptr(f), n, m, height, width, c,
+                                           C.ptr(composed), C.ptr(grid), C.dev_of(covs_c), C.stream_of(covs_c)))
+    return composed, grid
+
+
 def render_multiscale(xs, ys, covs, sizes, size: int, level_features: Sequence[Optional[torch.Tensor]],
                       out_dtype: torch.dtype):
     """blobsplat_render_multiscale: level l has size ``size >> l``; level_features[l] is [N, M+1, C_l] or None (maps only).

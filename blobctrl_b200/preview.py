@@ -73,6 +73,10 @@ class GraphedBlobRenderer:
                 self.grid, self.scores = ops.render_preview(self.xs, self.ys, self.covs, self.sizes, self.colors, self.h, self.w,
                                                             want_composed=True)
                 return
+            if self.feats is not None and not C.f32_exact() and ops.small_render_applies(self.n, self.m, self.h, self.w, c):
+                # the same rule as splat_features: a single small image takes the CUDA-core latency kernel
+                self.scores, self.grid = ops.render_small(self.xs, self.ys, self.covs, self.sizes, self.feats, self.h, self.w)
+                return
             if self.feats is not None and c >= 64:
                 try:
                     self.scores, self.grid = ops.render_fused(self.xs, self.ys, self.covs, self.sizes, self.feats, self.h, self.w)

@@ -230,7 +230,13 @@ def splat_features(
             and isinstance(score_size, int) and interp_size == score_size and engine != "fma"
             and covs.dtype != torch.float64):
         try:
-            d, grid = ops.render_fused(xs, ys, covs, sizes, features, h, w, out_dtype=out_dtype or covs.dtype)
+            if (engine == "auto" and covs.dtype == torch.float32 and features.dtype == torch.float32
+                    and out_dtype in (None, torch.float32) and not C.f32_exact()
+                    and ops.small_render_applies(covs.shape[0], m, h, w, features.shape[-1])):
+                # ONE small image (the scripts' and the UI's case, BASELINE config 2): the CUDA-core latency kernel
+                d, grid = ops.render_small(xs, ys, covs, sizes, features, h, w)
+            else:
+                d, grid = ops.render_fused(xs, ys, covs, sizes, features, h, w, out_dtype=out_dtype or covs.dtype)
         except C.BlobSplatUnsupported:
             if engine == "tensor":
                 raise

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BLOBSPLAT_ABI_VERSION 3
+#define BLOBSPLAT_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define BLOBSPLAT_API __attribute__((visibility("default")))
@@ -265,6 +265,16 @@ BLOBSPLAT_API int blobsplat_conv_in_hoisted(const void* latents, const void* con
 BLOBSPLAT_API int blobsplat_render(const float* xs, const float* ys, const float* covs, const float* sizes,
                      const void* features, int feat_dtype, int N, int M, int H, int W, int C,
                      void* composed, void* grid, int out_dtype, int device, void* stream);
+
+/*
+ * (4a) the same render as a one-launch LATENCY kernel on CUDA cores, float32 only: for the single small renders the
+ *      reference's scripts and UI issue (scripts/blobctrl_inference.py:112-117, scripts/blobctrl_app.py:637-650; BASELINE
+ *      config 2).  No tensor memory, no operand staging, full-fp32 products and sums like the reference's einsum
+ *      (utils.py:77).  K = M + 1 <= 33 (BLOBSPLAT_E_UNSUPPORTED otherwise); composed may be NULL.
+ */
+BLOBSPLAT_API int blobsplat_render_small(const float* xs, const float* ys, const float* covs, const float* sizes,
+                           const float* features, int N, int M, int H, int W, int C,
+                           float* composed, float* grid, int device, void* stream);
 
 /*
  * (4b) the multi-resolution conditioning in ONE call (BASELINE configs[2]): level l has size S >> l.  Level 0 is (4);

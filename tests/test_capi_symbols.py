@@ -24,7 +24,7 @@ def test_header_declares_the_expected_entry_points():
     d = _declared()
     assert set(d) == {"blobsplat_abi_version", "blobsplat_get_caps", "blobsplat_last_error", "blobsplat_scores",
                       "blobsplat_scores_ellipse", "blobsplat_composite", "blobsplat_resize_bilinear", "blobsplat_pyramid",
-                      "blobsplat_feature_splat", "blobsplat_feature_splat_levels", "blobsplat_conditioning_fill", "blobsplat_residual_inject", "blobsplat_render", "blobsplat_render_multiscale",
+                      "blobsplat_feature_splat", "blobsplat_feature_splat_levels", "blobsplat_conditioning_fill", "blobsplat_residual_inject", "blobsplat_render", "blobsplat_render_small", "blobsplat_render_multiscale",
                       "blobsplat_preview", "blobsplat_preview_u8", "blobsplat_conv_in_weights", "blobsplat_conv_in_hoisted"}
 
 
@@ -52,7 +52,7 @@ def test_binding_matches_header_arity_and_abi_version():
 def test_caps_and_argument_validation_without_a_gpu():
     from blobctrl_b200 import _capi
     c = _capi.caps()
-    assert c.abi_version == _capi.ABI_VERSION == 3 and c.sm_arch == 100 and c.max_blobs >= 65536
+    assert c.abi_version == _capi.ABI_VERSION == 4 and c.sm_arch == 100 and c.max_blobs >= 65536
     L = _capi.lib()
     # invalid arguments are rejected before any CUDA call
     assert L.blobsplat_scores(None, None, None, None, 0, 1, 1, 0, 8, 0, None, 0, None, 0, 0, -1, None) == -1

@@ -1165,6 +1165,47 @@ def test_fused_pyramid_equals_the_pyramid_kernel(n, m, c, levels, dtype):
         assert torch.equal(comps[l], pyr[64 >> l]), f"graph replay: level {64 >> l}"
 
 
+@pytest.mark.parametrize("m,h,w,c", [(16, 64, 64, 320), (1, 64, 64, 1024), (32, 20, 36, 100), (8, 9, 7, 3), (0, 16, 16, 32),
+                                     (5, 33, 1, 65), (24, 128, 128, 48)])
+def test_one_image_latency_render_vs_oracle(m, h, w, c):
+    """blobsplat_render_small — the CUDA-core kernel single small float32 renders take under AUTO (BASELINE config 2): composed
+    maps within a last place of the stand-alone stages 1+2, grid within 1e-5 of the float64 oracle (full-fp32 products, so in fact
+    ~1e-7), ragged pixel / channel tiles, gated blobs, K = 1; and the reference-signature call routes to it."""
+    from blobctrl_b200 import ops
+    U = _impl()
+    if m == 0:                                                             # no blobs: the background owns every pixel
+        z = torch.zeros(1, 0, device=DEV)
+        feats = torch.randn(1, 1, c, generator=torch.Generator().manual_seed(5)).to(DEV)
+        comp, grid = ops.render_small(z, z, torch.zeros(1, 0, 2, 2, device=DEV), z, feats, h, w)
+        assert torch.equal(comp, torch.ones(1, 1, h, w, device=DEV))
+        assert torch.equal(grid, feats[0, 0].view(1, c, 1, 1).expand(1, c, h, w))
+        return
+    syn = blob_oracle.synthetic_blobs(1, m, seed=31 + m, c=c)
+    if m >= 5:
+        syn["sizes"][0, 2] = 0.0                                           # a gated blob (utils.py:165-172)
+    b = _blob(syn)
+    feats = torch.from_numpy(syn["features"]).to(DEV)
+    comp, grid = ops.render_small(b["xs"], b["ys"], b["covs"], b["sizes"], feats, h, w)
+    sc, _ = ops.render_scores(b["xs"], b["ys"], b["covs"], b["sizes"], h, w)
+    assert (comp - sc).abs().max().item() <= 5e-7          # same coefficients; the 4-pixel kernel steps u, v along x (last-place differences)
+    raw = blob_oracle.raw_scores(syn["xs"], syn["ys"], syn["covs"], syn["sizes"], h, w, np.float64)
+    _, d = blob_oracle.composite(raw)
+    want = np.einsum("nhwk,nkc->nchw", d, syn["features"].astype(np.float64))
+    close_scaled(_np(comp), np.moveaxis(d, -1, 1), 1e-5, "latency render: composed")
+    close_scaled(_np(grid), want, 1e-5, "latency render: grid")
+    assert np.abs(_np(grid) - want).max() <= 2e-6 * max(np.abs(want).max(), 1e-30)      # full fp32: far inside the bar
+    if h == w and ops.small_render_applies(1, m, h, w, c):
+        out = U.splat_features(**b, features=feats, score_size=h, interp_size=h, ret_layout=False)
+        assert torch.equal(out["feature_grid"], grid) and torch.equal(out["scores_pyramid"][h], comp)
+        forced = U.splat_features(**b, features=feats, score_size=h, interp_size=h, ret_layout=False, engine="tensor") if c >= 8 and m >= 1 else None
+        if forced is not None:
+            close_scaled(_np(forced["feature_grid"]), want, 1e-5, "tensor engine on the same image")
+    assert not ops.small_render_applies(2, m, h, w, c) and not ops.small_render_applies(1, 40, h, w, c)
+    with pytest.raises(Exception):
+        big = blob_oracle.synthetic_blobs(1, 40, seed=1, c=8)
+        ops.render_small(*[_cuda(big[k]) for k in ("xs", "ys", "covs", "sizes")], _cuda(big["features"]), 8, 8)
+
+
 def test_f32_exact_switch_keeps_float32_on_the_fma_engine(monkeypatch):
     """BLOBSPLAT_F32_EXACT=1: float32 stage 3 under AUTO runs on the FMA engine — bit-identical to
     engine='fma' — and splat_features gives the scores + FMA-splat result instead of the split-precision fused render."""
