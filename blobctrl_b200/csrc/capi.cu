@@ -375,7 +375,7 @@ int blobsplat_render(const float* xs, const float* ys, const float* covs, const 
 int blobsplat_render_small(const float* xs, const float* ys, const float* covs, const float* sizes, const float* features,
                            int N, int M, int H, int W, int C, float* composed, float* grid, int device, void* stream) {
   BS_CHECK_ARG(N >= 0 && M >= 0 && H >= 1 && W >= 1 && C >= 1, "bad shape N=%d M=%d H=%d W=%d C=%d", N, M, H, W, C);
-  BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535 && (C + 31) / 32 <= 65535, "shape too large");
+  BS_CHECK_ARG((long long)H * W < (1ll << 31) && N <= 65535 && (C + 15) / 16 <= 65535, "shape too large");
   if (N == 0) return BLOBSPLAT_OK;
   BS_CHECK_ARG(M == 0 || (xs && ys && covs && sizes), "NULL blob parameter pointer");
   BS_CHECK_ARG(features && grid, "NULL pointer");

@@ -5,9 +5,11 @@
 // At this size the fused tcgen05 render is a serial chain of small steps (profiles/latency_phases_r2.txt: 7.2 us in the
 // kernel, 4.5 of them before the first opacity is evaluated: TMEM allocation, K-major 2 x fp16 operand staging, MMA commit
 // round trips), while the arithmetic itself is 22 MFMA — a microsecond of the FP32 pipe.  Here
-//   CTA = 128 pixels (thread = pixel) x kRsCT channels of one image; grid = (pixel tiles, channel tiles, images)
+//   CTA = 128 pixels (thread = pixel) x CT channels of one image; grid = (pixel tiles, channel tiles, images); CT = 16, 32 or
+//         64, the narrowest that keeps the grid at <= 1024 CTAs (cfg2: 32 x 20 = 640 CTAs of 16 channels — 8.2 us as a graph
+//         replay against 10.3 / 12.3 us with 32 / 64 channels; the K = 2, C = 1024 splat prefers 32: profiles/ab_small_r2.txt)
 //   blob coefficients: one thread per blob, float64 whitening (common.cuh::make_blob_coef), in shared memory
-//   features [K, kRsCT] of the channel tile: a coalesced copy into shared memory, in flight during the coefficient math
+//   features [K, CT] of the channel tile: a coalesced copy into shared memory, in flight during the coefficient math
 //   stages 1+2: front-to-back walk, the composed weights d_k of the pixel stay in REGISTERS (K <= KMAX, unrolled)
 //   stage 3: acc[4 channels] += d_k * F[k][c..c+3] (one broadcast LDS.128 per 4 FFMA), full-fp32 products and sums like
 //            the reference's einsum; plane stores are 128-byte lines per warp
@@ -18,9 +20,9 @@
 namespace blobsplat {
 
 constexpr int kRsThreads = 128;
-constexpr int kRsCT = 32;          // channels per CTA: 64 x 64 x 320 channels = 32 x 10 = 320 CTAs, two per SM
+constexpr int kRsMaxCtas = 1024;
 
-template <int KMAX>
+template <int KMAX, int kRsCT>
 __global__ void __launch_bounds__(kRsThreads)
 render_small_kernel(const float* __restrict__ xs, const float* __restrict__ ys, const float* __restrict__ covs,
                     const float* __restrict__ sizes, const float* __restrict__ feats, int M, int H, int W, int C,
@@ -91,14 +93,25 @@ render_small_kernel(const float* __restrict__ xs, const float* __restrict__ ys, 
 // Envelope of the latency kernel: float32 in and out, K = M + 1 <= 33 planes (the weights of a pixel live in registers).
 bool render_small_supported(int K) { return K >= 1 && K <= 33; }
 
+template <int KMAX>
+static int launch_small(int ct, dim3 g, cudaStream_t st, const float* xs, const float* ys, const float* covs, const float* sizes,
+                        const float* feats, int M, int H, int W, int C, float* composed, float* grid) {
+  if (ct == 16) BS_CUDA(launch_pdl(render_small_kernel<KMAX, 16>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
+  else if (ct == 32) BS_CUDA(launch_pdl(render_small_kernel<KMAX, 32>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
+  else BS_CUDA(launch_pdl(render_small_kernel<KMAX, 64>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
+  return 0;
+}
+
 int render_small_dispatch(const float* xs, const float* ys, const float* covs, const float* sizes, const float* feats, int N,
                           int M, int H, int W, int C, float* composed, float* grid, cudaStream_t st) {
   const int K = M + 1, P = H * W;
-  const dim3 g((unsigned)((P + kRsThreads - 1) / kRsThreads), (unsigned)((C + kRsCT - 1) / kRsCT), (unsigned)N);
-  if (K <= 9) BS_CUDA(launch_pdl(render_small_kernel<9>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
-  else if (K <= 17) BS_CUDA(launch_pdl(render_small_kernel<17>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
-  else BS_CUDA(launch_pdl(render_small_kernel<33>, g, dim3(kRsThreads), 0, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid));
-  return 0;
+  const long long px_tiles = (P + kRsThreads - 1) / kRsThreads;
+  int ct = 16;                                                   // narrowest channel tile that keeps the grid small
+  while (ct < 64 && px_tiles * ((C + ct - 1) / ct) * N > kRsMaxCtas) ct <<= 1;
+  const dim3 g((unsigned)px_tiles, (unsigned)((C + ct - 1) / ct), (unsigned)N);
+  if (K <= 9) return launch_small<9>(ct, g, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid);
+  if (K <= 17) return launch_small<17>(ct, g, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid);
+  return launch_small<33>(ct, g, st, xs, ys, covs, sizes, feats, M, H, W, C, composed, grid);
 }
 
 }  // namespace blobsplat

@@ -233,9 +233,11 @@ def render_fused(xs, ys, covs, sizes, features: torch.Tensor, height: int, width
     return composed, grid
 
 
-SMALL_RENDER_MAX_K = 33            # planes whose per-pixel weights fit in registers (render_small.cu)
-SMALL_RENDER_MAX_WORK = 3 << 23    # P * K * C multiply-adds of ONE image (25 M) up to which the latency kernel is the faster one:
-                                   # 8-10 us against 10-14 us at 8-22 M, 14.5 against 10-12 us at 43 M (graph replays, B200)
+SMALL_RENDER_MAX_K = 17            # AUTO takes the latency kernel up to 17 planes (it renders up to 33: the per-pixel weights live
+                                   # in registers); with more blobs every channel tile's repeat of stages 1+2 outweighs the start-up it saves
+SMALL_RENDER_MAX_WORK = 3 << 23    # and up to 25 M multiply-adds (P * K * C) of the ONE image.  Graph replays on a B200, latency vs
+                                   # tensor kernel: cfg2 (22 M) 8.2 vs 12.1 us, K = 2 x C = 1024 8.2 vs 14.3, M = 8 at 128 x 128 x 64
+                                   # 6.2 vs 10.3, M = 4 at 256 x 256 x 64 10.3 vs 14.3; M = 32 x C = 160 12.3 vs 10.3 (profiles/ab_small_r2.txt)
 
 
 def small_render_applies(n: int, m: int, height: int, width: int, c: int) -> bool:

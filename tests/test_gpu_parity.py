@@ -1200,7 +1200,7 @@ def test_one_image_latency_render_vs_oracle(m, h, w, c):
         forced = U.splat_features(**b, features=feats, score_size=h, interp_size=h, ret_layout=False, engine="tensor") if c >= 8 and m >= 1 else None
         if forced is not None:
             close_scaled(_np(forced["feature_grid"]), want, 1e-5, "tensor engine on the same image")
-    assert not ops.small_render_applies(2, m, h, w, c) and not ops.small_render_applies(1, 40, h, w, c)
+    assert not ops.small_render_applies(2, m, h, w, c) and not ops.small_render_applies(1, 17, h, w, c)
     with pytest.raises(Exception):
         big = blob_oracle.synthetic_blobs(1, 40, seed=1, c=8)
         ops.render_small(*[_cuda(big[k]) for k in ("xs", "ys", "covs", "sizes")], _cuda(big["features"]), 8, 8)
