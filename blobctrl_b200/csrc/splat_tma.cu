@@ -41,7 +41,7 @@
 
 namespace blobsplat {
 
-#define ST_STAMP(role, i, k) do { if (p.dbg && blockIdx.x == p.dbg_cta && (i) < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); p.dbg[((role) * 64 + (i)) * 4 + (k)] = t_; } } while (0)
+#define ST_STAMP(role, i, k) do { if constexpr (kDbg) { if (k_dbg && blockIdx.x == p.dbg_cta && (i) < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_)); k_dbg[((role) * 64 + (i)) * 4 + (k)] = t_; } } } while (0)
 
 constexpr int kStMaxLevels = 4;
 constexpr int kStM = 128;                 // channels per item (MMA M)
@@ -175,9 +175,14 @@ __device__ __forceinline__ uint32_t st_pack(uint32_t a, uint32_t b) {        // 
   }
 }
 
-template <bool kBf16>
+// kDbg = false is the production kernel: line stores, no ablation switches, no timeline stamps — those knobs are compiled
+// out, because the kernel sits at its 168-register cap and every live knob costs the drain loop registers.  Any of
+// BLOBSPLAT_ST_STORE / BLOBSPLAT_ST_ABL / BLOBSPLAT_ST_DBG_PTR selects the kDbg = true instantiation.
+template <bool kBf16, bool kDbg>
 __global__ void __launch_bounds__(kStThreads, 1)
 splat_tma_kernel(const __grid_constant__ StParams p) {
+  const int k_abl = kDbg ? p.abl : 0, k_tma_store = kDbg ? p.tma_store : 0;
+  unsigned long long* const k_dbg = kDbg ? p.dbg : nullptr;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const stage = smem;                                                     // [8 warps][nbuf][4 KB], 1 KB aligned
   unsigned char* const s_ring = stage + (size_t)kStDrainWarps * p.nbuf * kStBoxBytes;    // [2][s_bytes]
@@ -204,7 +209,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
   pdl_launch_dependents();
   pdl_wait();                                            // the score maps may come from the previous kernel in the stream
 
-  if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[1024 + 2 * blockIdx.x] = t; }
+  if (k_dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); k_dbg[1024 + 2 * blockIdx.x] = t; }
   const int it_begin = st_range_begin(p, (int)blockIdx.x, (int)gridDim.x);
   const int it_end = st_range_begin(p, (int)blockIdx.x + 1, (int)gridDim.x);
   const int ksteps = p.Kp >> 4;
@@ -230,7 +235,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
         ST_STAMP(0, i, 0);
         if (f_pass > 0) mbar_wait_spin(&bars->f_free[fs], (uint32_t)((f_pass - 1) & 1));
         ST_STAMP(0, i, 1);
-        if ((p.abl & 4) && f_pass > 0) mbar_arrive(&bars->f_full[fs]);
+        if ((k_abl & 4) && f_pass > 0) mbar_arrive(&bars->f_full[fs]);
         else {
           mbar_expect_tx(&bars->f_full[fs], (uint32_t)(p.Kp * kStM * 2));
           const uint32_t dst = smem_u32(f_ring + (size_t)fs * p.f_bytes);
@@ -271,7 +276,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
         const uint64_t a_desc = desc_hi | (uint64_t)(f_base + (uint32_t)((fs * p.f_bytes) >> 4));
         const uint64_t b_desc = desc_hi | (uint64_t)(s_base + (uint32_t)((sb * p.s_bytes) >> 4));
         const uint32_t d_addr = tmem + (uint32_t)(slot * p.slot_cols);
-        for (int ks = 0; ks < ((p.abl & 2) ? 0 : ksteps); ++ks)    // 16 k rows = two 1 KB atoms (128 x 16 B) further into every block
+        for (int ks = 0; ks < ((k_abl & 2) ? 0 : ksteps); ++ks)    // 16 k rows = two 1 KB atoms (128 x 16 B) further into every block
           umma_ss(d_addr, a_desc + (uint64_t)(ks * 128), b_desc + (uint64_t)(ks * 128), idesc, ks > 0 ? 1u : 0u);
         tc_commit(&bars->f_free[fs]);
         tc_commit(&bars->d_full[slot]);
@@ -332,8 +337,8 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
         if (b >= b_hi) break;
         // store path of this box: 0 = line stores by the warp, 1 = TMA tensor store; mode 2 (hybrid) alternates, so the LSU
         // and the TMA unit each carry half of the bytes (box 0 of the staging ring is the line-store box, 1.. the TMA ring)
-        const bool via_tma = p.tma_store == 1 || (p.tma_store == 2 && (st_it & 1));
-        const int ring0 = p.tma_store == 2 ? 1 : 0, ring = p.nbuf - ring0;
+        const bool via_tma = k_tma_store == 1 || (k_tma_store == 2 && (st_it & 1));
+        const int ring0 = k_tma_store == 2 ? 1 : 0, ring = p.nbuf - ring0;
         const int sbuf = via_tma ? ring0 + t_it % ring : 0;
         if (via_tma && t_it >= ring) {                           // the TMA store that last read this box has drained it
           if (lane == 0) {
@@ -345,7 +350,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
         }
         unsigned char* const box = my_stage + (size_t)sbuf * kStBoxBytes;
         unsigned char* const row = box + lane * 128;
-        if (!(p.abl & 8))
+        if (!(k_abl & 8))
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           *reinterpret_cast<uint4*>(row + ((c ^ (lane & 7)) << 4)) =
@@ -355,7 +360,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            if (!(p.abl & 1)) tma_store_3d(&L.out, smem_u32(box), px_tile + b * kStBoxPx, it.group * kStM + q * kStBoxCh, it.n);
+            if (!(k_abl & 1)) tma_store_3d(&L.out, smem_u32(box), px_tile + b * kStBoxPx, it.group * kStM + q * kStBoxCh, it.n);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++t_it;
@@ -367,7 +372,7 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
           const int px = px_tile + b * kStBoxPx + ((lane & 7) << 3);
           unsigned char* const o = reinterpret_cast<unsigned char*>(const_cast<void*>(p.out_ptr[it.level])) +
                                    (((size_t)it.n * C + ch0) * L.P + px) * 2;
-          const bool px_ok = px < L.P && !(p.abl & 1);
+          const bool px_ok = px < L.P && !(k_abl & 1);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int rr = 4 * j + (lane >> 3);
@@ -383,13 +388,13 @@ splat_tma_kernel(const __grid_constant__ StParams p) {
       it.advance(p);
       if (item + 1 < it_end) it.advance(p);
     }
-    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (k_tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     __syncwarp();
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); p.dbg[1025 + 2 * blockIdx.x] = t; }
+  if (k_dbg && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); k_dbg[1025 + 2 * blockIdx.x] = t; }
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols) : "memory");
   }
@@ -464,8 +469,10 @@ int splat_tma_dispatch(int n_levels, const void* const* scores, const int64_t* s
   int dev = 0;
   BS_CUDA(cudaGetDevice(&dev));
   if (configured_dev != dev) {
-    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    BS_CUDA(cudaFuncSetAttribute(splat_tma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     BS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     configured_dev = dev;
   }
@@ -530,8 +537,14 @@ int splat_tma_dispatch(int n_levels, const void* const* scores, const int64_t* s
   const size_t smem = (size_t)kStDrainWarps * p.nbuf * kStBoxBytes + (size_t)p.ns * p.s_bytes + (size_t)p.nf * p.f_bytes +
                       sizeof(StBarriers) + 64;
   const int grid = std::min(sm_count, items);
-  if (dtype == BLOBSPLAT_BF16) BS_CUDA(launch_pdl(splat_tma_kernel<true>, dim3(grid), dim3(kStThreads), smem, st, p));
-  else BS_CUDA(launch_pdl(splat_tma_kernel<false>, dim3(grid), dim3(kStThreads), smem, st, p));
+  const bool dbg = p.tma_store != 0 || p.abl != 0 || p.dbg != nullptr;            // measurement knobs: the instrumented instantiation
+  if (dbg) {
+    if (dtype == BLOBSPLAT_BF16) BS_CUDA(launch_pdl(splat_tma_kernel<true, true>, dim3(grid), dim3(kStThreads), smem, st, p));
+    else BS_CUDA(launch_pdl(splat_tma_kernel<false, true>, dim3(grid), dim3(kStThreads), smem, st, p));
+  } else {
+    if (dtype == BLOBSPLAT_BF16) BS_CUDA(launch_pdl(splat_tma_kernel<true, false>, dim3(grid), dim3(kStThreads), smem, st, p));
+    else BS_CUDA(launch_pdl(splat_tma_kernel<false, false>, dim3(grid), dim3(kStThreads), smem, st, p));
+  }
   return 0;
 }
 
