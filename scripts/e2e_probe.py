@@ -17,7 +17,7 @@ def timed(f, reps=20):
     return a.elapsed_time(b) / reps
 t = timed(lambda: dev_f.copy_(pf, non_blocking=True))
 print(f"raw H2D of the features ({pf.numel()*4/1e6:.1f} MB): {t:.3f} ms = {pf.numel()*4/t/1e6:.1f} GB/s")
-for sets in (1, 2):
-    for chunks in (2, 4, 8, 16, 32):
+for sets in (2,):
+    for chunks in (1, 2, 3, 4, 6, 8):
         r = HostRenderer(1024, 64, 64, 320, torch.float32, "cuda", chunks=chunks, input_sets=sets)
         print(f"HostRenderer input_sets={sets} chunks={chunks}: {timed(lambda: r(pin['xs'], pin['ys'], pin['covs'], pin['sizes'], pf)):.3f} ms")
