@@ -295,8 +295,11 @@ def main():
 
     # this rank's image shard (weak scaling: N_IMG images per GPU, seeded per rank)
     host_blobs, host_feats = synthetic(N_IMG, M_BLOBS, CHANNELS, seed=rank)
-    pin = {k: v.pin_memory() for k, v in host_blobs.items()}
-    pin_feats = host_feats.pin_memory()
+    # host inputs of the e2e path: page-locked; BLOBSPLAT_BENCH_WC=1 allocates them write-combined (blobctrl_b200.hostmem)
+    wc_inputs = os.environ.get("BLOBSPLAT_BENCH_WC", "0") == "1"
+    from blobctrl_b200.hostmem import pinned_like
+    pin = pinned_like(host_blobs, write_combined=wc_inputs)
+    pin_feats = pinned_like({"f": host_feats}, write_combined=wc_inputs)["f"]
     blobs = {k: v.to(dev) for k, v in host_blobs.items()}
     feats = host_feats.to(dev)
     P = SIZE * SIZE
@@ -375,6 +378,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_total / args.steps * 1e3,
                     "what": "H2D of all inputs + render + D2H of the last image's maps (a sample of the result)",
+                    "host_inputs": "pinned, write-combined" if wc_inputs else "pinned",
                     "h2d_probe": {"ms_per_step": h2d_total / args.steps * 1e3,
                                   "aggregate_GBs": h2d * world / (h2d_total / args.steps) / 1e9,
                                   "per_gpu_GBs": h2d / (h2d_total / args.steps) / 1e9,

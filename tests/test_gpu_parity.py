@@ -1243,3 +1243,24 @@ def test_fused_float32_render_across_feature_magnitudes(scale):
     got, ref = _np(grid), want["feature_grid"]
     for i in range(n):                                  # per image: each has its own magnitude
         close_scaled(got[i], ref[i], 1e-5, f"image {i} (feature scale {float(per_image[i, 0, 0]):g})")
+
+
+def test_write_combined_pinned_inputs_round_trip():
+    """blobctrl_b200.hostmem: cudaHostAllocWriteCombined buffers are seen as pinned by torch, feed HostRenderer like
+    ordinary pinned tensors (same maps, bit for bit) and are released explicitly."""
+    from blobctrl_b200 import hostmem
+    from blobctrl_b200.streaming import HostRenderer
+    n, m, s, c = 8, 5, 32, 64
+    syn = blob_oracle.synthetic_blobs(n, m, seed=77, c=c)
+    host = {k: torch.from_numpy(v) for k, v in syn.items()}
+    wc = hostmem.pinned_like(host, write_combined=True)
+    pl = hostmem.pinned_like(host, write_combined=False)
+    assert all(t.is_pinned() for t in wc.values()) and all(t.is_pinned() for t in pl.values())
+    r = HostRenderer(n, m, s, c, torch.float32, DEV, chunks=2)
+    a = r(wc["xs"], wc["ys"], wc["covs"], wc["sizes"], wc["features"])
+    a = (a["scores_pyramid"][s].clone(), a["feature_grid"].clone())
+    b = r(pl["xs"], pl["ys"], pl["covs"], pl["sizes"], pl["features"])
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b["scores_pyramid"][s]) and torch.equal(a[1], b["feature_grid"])
+    for t in wc.values():
+        hostmem.free_pinned(t)
