@@ -530,6 +530,8 @@ def variants(B, ops, dev, peak):
         by = algorithmic_bytes(n, m, P, 0, 4, 4, grid=False)
         out[f"cfg5a_scores_fp32_{mode}"] = {"ms": ms, "Mpxblob_s": n * m * P / ms / 1e3, "GBs": by / ms / 1e6,
                                             "frac": by / ms / 1e6 / peak}
+    out["cfg5a_scores_fp32_warp_scan"]["note"] = ("lane = blob suffix scan (BLOBSPLAT_COMPOSITE_WARP_SCAN): an explicit opt-in mode "
+                                                  "kept for A/B; AUTO never selects it (lane = pixel is faster at every shape)")
     try:
         fb = feats.to(torch.bfloat16)
         ms = timed(lambda: B.splat_features(**blobs, features=fb, score_size=SIZE, interp_size=SIZE, ret_layout=False,
