@@ -20,12 +20,19 @@ _live = {}                                   # data_ptr -> cudart handle: freed 
 
 
 def _cudart():
-    for name in ("libcudart.so.12", "libcudart.so"):
+    """The CUDA runtime torch already loaded (by soname), else the wheel's or the toolkit's copy.  Any instance will do:
+    they share the device's primary context, and pinned allocations are visible to every runtime in the process."""
+    import glob
+    import os
+    names = ["libcudart.so.12", "libcudart.so"]
+    names += glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+    names += glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+    for name in names:
         try:
             return ctypes.CDLL(name)
         except OSError:
             continue
-    raise RuntimeError("libcudart not found: import torch with CUDA first")
+    raise RuntimeError("libcudart not found (tried the loaded runtime, torch's wheel and /usr/local/cuda)")
 
 
 def pinned_empty(shape, dtype=torch.float32, write_combined: bool = False) -> torch.Tensor:
