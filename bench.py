@@ -191,7 +191,7 @@ def workload_config(n_gpus):
                         f"(BASELINE.json configs[4]; largest single-GPU config)",
             "images_per_gpu": N_IMG, "blobs": M_BLOBS, "size": SIZE, "channels": CHANNELS, "sharding": f"by-image x{n_gpus}",
             "l2": "outputs 6.5 GB/step stream through the 126 MB L2 (>> L2); the 87 MB of inputs are re-read each step",
-            "e2e_pipeline": "H2D + render + sample D2H — HostRenderer: pinned H2D in 4 chunks on a copy stream, double-buffered "
+            "e2e_pipeline": "H2D + render + sample D2H — HostRenderer: pinned H2D on a copy stream (parameters whole, features in 4 chunks), double-buffered "
                             "staging (the copies of step i+1 overlap the renders of step i), D2H of the LAST IMAGE's maps every "
                             "step (6.3 MB of the 6.46 GB result; the maps are consumed on the device).  e2e.full_d2h copies the "
                             "whole result back instead"}
